@@ -1,0 +1,786 @@
+"""Horovod-style collective frontend used inside a pickled ``main``.
+
+The reference *is* "run Horovod" (``/root/reference/sparkdl/horovod/runner_base.py:24-25``) but
+ships no frontend: ``hvd.init()`` in the user's main is expected to find its peers
+(SURVEY.md §1b "Rendezvous + Horovod runtime").  This module is that frontend, written from
+scratch for one B200 box:
+
+* CPU tensors  -> C++ engine + POSIX-shm collectives (``csrc/core``);
+* CUDA tensors -> the same engine negotiates names / fusion, then launches hand-written
+  sm_100a peer-memory kernels (``csrc/cuda``) on a communication stream - no NCCL call.
+
+Usage (same names as ``horovod.torch``)::
+
+    import sparkdl.hvd as hvd
+    hvd.init()
+    opt = hvd.DistributedOptimizer(opt, named_parameters=model.named_parameters())
+    hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+"""
+import io
+import os
+import pickle
+import threading
+import uuid
+
+import torch
+
+from spark_deep_learning_b200.parallel import context as _context
+from spark_deep_learning_b200.parallel import core as _core
+from spark_deep_learning_b200.utils.config import get_config
+
+# reduce-op constants (values match csrc/core/common.h ReduceOp where applicable)
+Average = _core.OP_AVERAGE
+Sum = _core.OP_SUM
+Min = _core.OP_MIN
+Max = _core.OP_MAX
+Product = _core.OP_PRODUCT
+Adasum = 100
+
+_DTYPES = {
+    torch.uint8: _core.U8, torch.int8: _core.I8, torch.int32: _core.I32, torch.int64: _core.I64,
+    torch.float16: _core.F16, torch.bfloat16: _core.BF16, torch.float32: _core.F32,
+    torch.float64: _core.F64, torch.bool: _core.BOOL,
+}
+_FLOATS = (torch.float16, torch.bfloat16, torch.float32, torch.float64)
+
+
+class HorovodInternalError(RuntimeError):
+    """A collective failed (mismatched submissions, a dead peer, a stall)."""
+
+
+class _State(object):
+    def __init__(self):
+        self.initialized = False
+        self.ctx = None
+        self.cfg = None
+        self.engine = None
+        self.comm = None          # ops.comm.SymmComm when CUDA is in use
+        self.counters = {}
+        self.lock = threading.Lock()
+
+
+_S = _State()
+
+
+# ---------------------------------------------------------------------------------------------
+# lifecycle
+# ---------------------------------------------------------------------------------------------
+def init(comm=None, process_sets=None):  # pylint: disable=unused-argument
+    """Join the gang started by :class:`sparkdl.HorovodRunner` (or torchrun) and start the engine.
+
+    On a GPU box this also pins the process to ``cuda:local_rank`` and exchanges CUDA VMM/IPC
+    handles, signal pads and the NVSwitch multicast object with the peers
+    (BASELINE.json north star: "exchanges cudaIpc/fabric handles and NVLink topology at init").
+    """
+    with _S.lock:
+        if _S.initialized:
+            return
+        cfg = get_config(refresh=True)
+        ctx = _context.get_context()
+        use_cuda = torch.cuda.is_available() and os.environ.get("SPARKDL_FORCE_CPU") != "1"
+        if use_cuda:
+            torch.cuda.set_device(ctx.local_rank % torch.cuda.device_count())
+        if ctx.rank == 0:
+            shm_name = "/sparkdl-%s-%s" % (ctx.job_id[:40], uuid.uuid4().hex[:8])
+            ctx.store.set("shm_name", shm_name)
+        else:
+            shm_name = ctx.store.get("shm_name", cfg.start_timeout_s)
+        _S.engine = _core.CoreEngine(shm_name, ctx.rank, ctx.size, cfg)
+        _S.ctx, _S.cfg = ctx, cfg
+        _S.counters = {}
+        if use_cuda:
+            from spark_deep_learning_b200.ops import comm as _comm
+            _S.comm = _comm.SymmComm(ctx, cfg)
+            fn, cctx = _S.comm.engine_executor()
+            _S.engine.set_gpu_executor(fn, cctx)
+        _S.initialized = True
+
+
+def shutdown():
+    with _S.lock:
+        if not _S.initialized:
+            return
+        _S.initialized = False
+        try:
+            if _S.comm is not None:
+                _S.comm.close()
+        finally:
+            _S.comm = None
+            try:
+                _S.engine.shutdown()
+            finally:
+                _S.engine = None
+                _context.reset_context()
+                _S.ctx = None
+
+
+def is_initialized():
+    return _S.initialized
+
+
+def _require():
+    if not _S.initialized:
+        raise ValueError("sparkdl.hvd has not been initialized; use hvd.init().")
+
+
+def size():
+    _require()
+    return _S.ctx.size
+
+
+def rank():
+    _require()
+    return _S.ctx.rank
+
+
+def local_rank():
+    _require()
+    return _S.ctx.local_rank
+
+
+def local_size():
+    _require()
+    return _S.ctx.local_size
+
+
+def cross_rank():
+    _require()
+    return 0
+
+
+def cross_size():
+    _require()
+    return 1
+
+
+def is_homogeneous():
+    return True
+
+
+def mpi_threads_supported():
+    return False
+
+
+def mpi_enabled():
+    return False
+
+
+def mpi_built():
+    return False
+
+
+def gloo_enabled():
+    return False
+
+
+def gloo_built():
+    return False
+
+
+def nccl_built():
+    return 0  # by design: the data plane is our own sm_100a kernels, not NCCL
+
+
+def ddl_built():
+    return False
+
+
+def ccl_built():
+    return False
+
+
+def cuda_built():
+    return torch.cuda.is_available()
+
+
+def rocm_built():
+    return False
+
+
+def comm_backend():
+    """The CUDA symmetric-memory communicator (``None`` on a CPU-only gang)."""
+    _require()
+    return _S.comm
+
+
+def engine_stats():
+    _require()
+    return _S.engine.stats()
+
+
+# ---------------------------------------------------------------------------------------------
+# compression (wire dtype != storage dtype)
+# ---------------------------------------------------------------------------------------------
+class _NoneCompressor(object):
+    @staticmethod
+    def compress(tensor):
+        return tensor, None
+
+    @staticmethod
+    def decompress(tensor, ctx):  # pylint: disable=unused-argument
+        return tensor
+
+
+class _CastCompressor(object):
+    wire = torch.float16
+
+    @classmethod
+    def compress(cls, tensor):
+        if tensor.dtype in (torch.float32, torch.float64):
+            return tensor.to(cls.wire), tensor.dtype
+        return tensor, None
+
+    @staticmethod
+    def decompress(tensor, ctx):
+        return tensor if ctx is None else tensor.to(ctx)
+
+
+class _FP16Compressor(_CastCompressor):
+    wire = torch.float16
+
+
+class _BF16Compressor(_CastCompressor):
+    wire = torch.bfloat16
+
+
+class Compression(object):
+    """Gradient compression for allreduce (``hvd.Compression.fp16`` as in Horovod)."""
+    none = _NoneCompressor
+    fp16 = _FP16Compressor
+    bf16 = _BF16Compressor
+
+
+# ---------------------------------------------------------------------------------------------
+# handles
+# ---------------------------------------------------------------------------------------------
+class _Handle(object):
+    __slots__ = ("hs", "output", "keep", "post", "cuda", "done", "result")
+
+    def __init__(self, hs, output, keep, post=None, cuda=False):
+        self.hs = hs
+        self.output = output
+        self.keep = keep
+        self.post = post
+        self.cuda = cuda
+        self.done = False
+        self.result = None
+
+
+def _auto_name(kind, name):
+    if name is not None:
+        return "%s.%s" % (kind, name)
+    n = _S.counters.get(kind, 0)
+    _S.counters[kind] = n + 1
+    return "%s.noname.%d" % (kind, n)
+
+
+def _dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise ValueError("sparkdl.hvd does not support tensors of dtype %s" % t.dtype)
+
+
+def _device_of(t):
+    return t.device.index if t.is_cuda else -1
+
+
+def _ready_event(t):
+    """CUDA tensors: event recorded on the producer stream so the comm stream can order itself
+    after the kernels that wrote ``t``."""
+    if not t.is_cuda:
+        return 0
+    return _S.comm.record_ready_event()
+
+
+def _enqueue(req, name, t_in, t_out, op=_core.OP_SUM, root=0, pre=1.0, post=1.0, splits=None,
+             shape=None):
+    return _S.engine.enqueue(req, name, _dtype_code(t_in), _device_of(t_in), op, root,
+                             list(t_in.shape if shape is None else shape), pre, post,
+                             t_in.data_ptr(), t_out.data_ptr() if t_out is not None else 0,
+                             splits, _ready_event(t_in))
+
+
+def poll(handle):
+    """True when :func:`synchronize` would not block on the host."""
+    _require()
+    return all(_S.engine.poll(h) != 0 for h in handle.hs)
+
+
+def synchronize(handle):
+    """Wait for an asynchronous collective and return its output tensor.
+
+    For CUDA tensors the host only waits until the kernel has been *launched*; the calling
+    stream is then made to wait for the completion event, so no host-device sync happens.
+    """
+    _require()
+    if handle.done:
+        return handle.result
+    try:
+        for h in handle.hs:
+            try:
+                _S.engine.wait(h)
+            except _core.EngineError as e:
+                raise HorovodInternalError(str(e))
+            if handle.cuda:
+                ev = _S.engine.done_event(h)
+                if ev:
+                    _S.comm.current_stream_wait(ev)
+        out = handle.output
+        if handle.post is not None:
+            out = handle.post(handle)
+    finally:
+        for h in handle.hs:
+            _S.engine.release(h)
+    handle.done = True
+    handle.result = out
+    handle.keep = None
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# allreduce
+# ---------------------------------------------------------------------------------------------
+def _resolve_op(average, op):
+    if average is not None and op is not None:
+        raise ValueError("The op parameter supersedes average. Please provide only one of them.")
+    if op is None:
+        op = Average if (average is None or average) else Sum
+    if op == Adasum:
+        raise NotImplementedError("Adasum is not supported by the sm_100a runtime")
+    return op
+
+
+def _allreduce_async_impl(tensor, output, name, op, prescale, postscale):
+    _require()
+    if op == Average:
+        if tensor.dtype in _FLOATS:
+            op, postscale = Sum, postscale / float(size())
+            int_avg = False
+        else:
+            op, int_avg = Sum, True
+    else:
+        int_avg = False
+    src = tensor if tensor.is_contiguous() else tensor.contiguous()
+    dst = output if (output.is_contiguous() and output.dtype == src.dtype) else torch.empty_like(src)
+    h = _enqueue(_core.ALLREDUCE, name, src, dst, op=op, pre=prescale, post=postscale)
+
+    def post(hd, _dst=dst, _out=output, _int_avg=int_avg):
+        if _int_avg:
+            _dst.copy_(torch.div(_dst, size(), rounding_mode="floor"))
+        if _dst is not _out:
+            _out.copy_(_dst)
+        return _out
+    return _Handle([h], output, (src, dst, tensor), post, tensor.is_cuda)
+
+
+def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.0,
+                    postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    op = _resolve_op(average, op)
+    output = torch.empty_like(tensor, memory_format=torch.contiguous_format)
+    return _allreduce_async_impl(tensor, output, _auto_name("allreduce", name), op,
+                                 prescale_factor, postscale_factor)
+
+
+def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1.0,
+                     postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    op = _resolve_op(average, op)
+    return _allreduce_async_impl(tensor, tensor, _auto_name("allreduce", name), op,
+                                 prescale_factor, postscale_factor)
+
+
+class _AllreduceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tensor, average, name, op, pre, post):
+        ctx.args = (average, op, pre, post)
+        return synchronize(allreduce_async(tensor, average, name, op, pre, post))
+
+    @staticmethod
+    def backward(ctx, grad):
+        average, op, pre, post = ctx.args
+        return allreduce(grad.contiguous(), average=average, op=op, prescale_factor=pre,
+                         postscale_factor=post), None, None, None, None, None
+
+
+def allreduce(tensor, average=None, name=None, compression=Compression.none, op=None,
+              prescale_factor=1.0, postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    """Average (default) or reduce ``tensor`` over all ranks; returns a new tensor.
+
+    Differentiable: the gradient of an allreduce is the allreduce of the gradient."""
+    comp, cctx = compression.compress(tensor)
+    if comp.requires_grad and torch.is_grad_enabled():
+        out = _AllreduceFn.apply(comp, average, name, op, prescale_factor, postscale_factor)
+    else:
+        out = synchronize(allreduce_async(comp, average, name, op, prescale_factor, postscale_factor))
+    return compression.decompress(out, cctx)
+
+
+def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
+               process_set=None):  # pylint: disable=unused-argument
+    return synchronize(allreduce_async_(tensor, average, name, op, prescale_factor, postscale_factor))
+
+
+def grouped_allreduce_async(tensors, average=None, name=None, op=None, prescale_factor=1.0,
+                            postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    """All tensors of the group are submitted together, so the engine fuses them into one
+    launch whenever dtype/op agree and they fit the fusion threshold."""
+    op = _resolve_op(average, op)
+    base = _auto_name("grouped_allreduce", name)
+    subs = []
+    for i, t in enumerate(tensors):
+        out = torch.empty_like(t, memory_format=torch.contiguous_format)
+        subs.append(_allreduce_async_impl(t, out, "%s.%d" % (base, i), op, prescale_factor,
+                                          postscale_factor))
+    return _group(subs)
+
+
+def grouped_allreduce_async_(tensors, average=None, name=None, op=None, prescale_factor=1.0,
+                             postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    op = _resolve_op(average, op)
+    base = _auto_name("grouped_allreduce", name)
+    subs = [_allreduce_async_impl(t, t, "%s.%d" % (base, i), op, prescale_factor, postscale_factor)
+            for i, t in enumerate(tensors)]
+    return _group(subs)
+
+
+def _group(subs):
+    def post(hd, _subs=subs):
+        return [synchronize(s) for s in _subs]
+    return _Handle([], None, subs, post, False)
+
+
+def grouped_allreduce(tensors, average=None, name=None, compression=Compression.none, op=None,
+                      prescale_factor=1.0, postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    pairs = [compression.compress(t) for t in tensors]
+    outs = synchronize(grouped_allreduce_async([p[0] for p in pairs], average, name, op,
+                                               prescale_factor, postscale_factor))
+    return [compression.decompress(o, p[1]) for o, p in zip(outs, pairs)]
+
+
+def grouped_allreduce_(tensors, average=None, name=None, op=None, prescale_factor=1.0,
+                       postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    return synchronize(grouped_allreduce_async_(tensors, average, name, op, prescale_factor,
+                                                postscale_factor))
+
+
+# ---------------------------------------------------------------------------------------------
+# allgather
+# ---------------------------------------------------------------------------------------------
+def _host_allgather_ints(values, name):
+    """Small host-side allgather of a python int list (sizes, splits)."""
+    t = torch.tensor(list(values), dtype=torch.int64).reshape(1, -1)
+    h = _enqueue(_core.ALLGATHER, name, t, None)
+    try:
+        _S.engine.wait(h)
+        out = torch.empty((_S.engine.out_dim0(h), t.shape[1]), dtype=torch.int64)
+        _S.engine.copy_out(h, out.data_ptr())
+    except _core.EngineError as e:
+        raise HorovodInternalError(str(e))
+    finally:
+        _S.engine.release(h)
+    return out
+
+
+def allgather_async(tensor, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Concatenate ``tensor`` from all ranks along dim 0 (dim 0 may differ per rank)."""
+    _require()
+    name = _auto_name("allgather", name)
+    src = tensor.contiguous()
+    if src.dim() == 0:
+        src = src.reshape(1)
+    if src.is_cuda:
+        sizes = _host_allgather_ints([src.shape[0]], name + ".dim0").reshape(-1).tolist()
+        out = torch.empty((sum(sizes),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        h = _enqueue(_core.ALLGATHER, name, src, out)
+        return _Handle([h], out, (src, out), None, True)
+    h = _enqueue(_core.ALLGATHER, name, src, None)
+
+    def post(hd, _src=src, _h=h):
+        out = torch.empty((_S.engine.out_dim0(_h),) + tuple(_src.shape[1:]), dtype=_src.dtype)
+        _S.engine.copy_out(_h, out.data_ptr())
+        return out
+    return _Handle([h], None, (src,), post, False)
+
+
+class _AllgatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tensor, name):
+        ctx.dim0 = tensor.shape[0] if tensor.dim() > 0 else 1
+        sizes = _host_allgather_ints([ctx.dim0], _auto_name("allgather.bwd_sizes", None))
+        ctx.offset = int(sizes.reshape(-1)[:rank()].sum())
+        return synchronize(allgather_async(tensor, name))
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = allreduce(grad.contiguous(), op=Sum)
+        return g.narrow(0, ctx.offset, ctx.dim0), None
+
+
+def allgather(tensor, name=None, process_set=None):  # pylint: disable=unused-argument
+    if tensor.requires_grad and torch.is_grad_enabled():
+        return _AllgatherFn.apply(tensor, name)
+    return synchronize(allgather_async(tensor, name))
+
+
+def grouped_allgather(tensors, name=None, process_set=None):  # pylint: disable=unused-argument
+    base = _auto_name("grouped_allgather", name)
+    hs = [allgather_async(t, "%s.%d" % (base, i)) for i, t in enumerate(tensors)]
+    return [synchronize(h) for h in hs]
+
+
+# ---------------------------------------------------------------------------------------------
+# broadcast
+# ---------------------------------------------------------------------------------------------
+def _broadcast_async_impl(tensor, output, root_rank, name):
+    _require()
+    if not 0 <= root_rank < size():
+        raise ValueError("root_rank %d out of range for size %d" % (root_rank, size()))
+    src = tensor if tensor.is_contiguous() else tensor.contiguous()
+    dst = output if output.is_contiguous() else torch.empty_like(src)
+    if dst is not src and rank() == root_rank:
+        dst.copy_(src)
+    h = _enqueue(_core.BROADCAST, name, dst, dst, root=root_rank)
+
+    def post(hd, _dst=dst, _out=output):
+        if _dst is not _out:
+            _out.copy_(_dst)
+        return _out
+    return _Handle([h], output, (src, dst, tensor), post, tensor.is_cuda)
+
+
+def broadcast_async(tensor, root_rank, name=None, process_set=None):  # pylint: disable=unused-argument
+    output = torch.empty_like(tensor, memory_format=torch.contiguous_format)
+    return _broadcast_async_impl(tensor, output, root_rank, _auto_name("broadcast", name))
+
+
+def broadcast_async_(tensor, root_rank, name=None, process_set=None):  # pylint: disable=unused-argument
+    return _broadcast_async_impl(tensor, tensor, root_rank, _auto_name("broadcast", name))
+
+
+class _BroadcastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tensor, root_rank, name):
+        ctx.root = root_rank
+        return synchronize(broadcast_async(tensor, root_rank, name))
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = allreduce(grad.contiguous(), op=Sum)
+        if rank() != ctx.root:
+            g = g * 0
+        return g, None, None
+
+
+def broadcast(tensor, root_rank, name=None, process_set=None):  # pylint: disable=unused-argument
+    if tensor.requires_grad and torch.is_grad_enabled():
+        return _BroadcastFn.apply(tensor, root_rank, name)
+    return synchronize(broadcast_async(tensor, root_rank, name))
+
+
+def broadcast_(tensor, root_rank, name=None, process_set=None):  # pylint: disable=unused-argument
+    return synchronize(broadcast_async_(tensor, root_rank, name))
+
+
+# ---------------------------------------------------------------------------------------------
+# alltoall / reducescatter
+# ---------------------------------------------------------------------------------------------
+def alltoall_async(tensor, splits=None, name=None, process_set=None):  # pylint: disable=unused-argument
+    _require()
+    name = _auto_name("alltoall", name)
+    src = tensor.contiguous()
+    if src.dim() == 0:
+        raise ValueError("alltoall needs a tensor with at least one dimension")
+    want_splits = splits is not None
+    if splits is None:
+        if src.shape[0] % size() != 0:
+            raise ValueError("tensor first dimension must be divisible by size() when splits is None")
+        sp = [src.shape[0] // size()] * size()
+    else:
+        sp = [int(s) for s in (splits.tolist() if torch.is_tensor(splits) else splits)]
+        if len(sp) != size() or sum(sp) != src.shape[0]:
+            raise ValueError("splits must have size() entries that sum to tensor.shape[0]")
+    if src.is_cuda:
+        matrix = _host_allgather_ints(sp, name + ".splits")            # [src, dst]
+        recv = matrix[:, rank()].tolist()
+        out = torch.empty((sum(recv),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        h = _enqueue(_core.ALLTOALL, name, src, out, splits=sp)
+        rs = torch.tensor(recv, dtype=torch.int32)
+
+        def post_c(hd, _out=out, _rs=rs):
+            return (_out, _rs) if want_splits else _out
+        return _Handle([h], out, (src, out), post_c, True)
+    h = _enqueue(_core.ALLTOALL, name, src, None, splits=sp)
+
+    def post(hd, _src=src, _h=h):
+        out = torch.empty((_S.engine.out_dim0(_h),) + tuple(_src.shape[1:]), dtype=_src.dtype)
+        _S.engine.copy_out(_h, out.data_ptr())
+        if want_splits:
+            return out, torch.tensor(_S.engine.recv_splits(_h), dtype=torch.int32)
+        return out
+    return _Handle([h], None, (src,), post, False)
+
+
+def alltoall(tensor, splits=None, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Rank r sends ``splits[d]`` rows to rank d and receives the rows addressed to it."""
+    return synchronize(alltoall_async(tensor, splits, name))
+
+
+def reducescatter_async(tensor, name=None, op=Average, prescale_factor=1.0, postscale_factor=1.0,
+                        process_set=None):  # pylint: disable=unused-argument
+    _require()
+    name = _auto_name("reducescatter", name)
+    if op == Average:
+        op, postscale_factor = Sum, postscale_factor / float(size())
+    src = tensor.contiguous()
+    if src.dim() == 0:
+        raise ValueError("reducescatter needs a tensor with at least one dimension")
+    d0 = src.shape[0]
+    rows = d0 // size() + (1 if rank() < d0 % size() else 0)
+    if src.is_cuda:
+        out = torch.empty((rows,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        h = _enqueue(_core.REDUCESCATTER, name, src, out, op=op, pre=prescale_factor,
+                     post=postscale_factor)
+        return _Handle([h], out, (src, out), None, True)
+    h = _enqueue(_core.REDUCESCATTER, name, src, None, op=op, pre=prescale_factor,
+                 post=postscale_factor)
+
+    def post(hd, _src=src, _h=h, _rows=rows):
+        out = torch.empty((_rows,) + tuple(_src.shape[1:]), dtype=_src.dtype)
+        _S.engine.copy_out(_h, out.data_ptr())
+        return out
+    return _Handle([h], None, (src,), post, False)
+
+
+def reducescatter(tensor, name=None, op=Average, prescale_factor=1.0, postscale_factor=1.0,
+                  process_set=None):  # pylint: disable=unused-argument
+    """Reduce over ranks, then rank r keeps the r-th slice of dim 0 (remainder rows go to the
+    lowest ranks)."""
+    return synchronize(reducescatter_async(tensor, name, op, prescale_factor, postscale_factor))
+
+
+def grouped_reducescatter(tensors, name=None, op=Average, process_set=None):  # pylint: disable=unused-argument
+    base = _auto_name("grouped_reducescatter", name)
+    hs = [reducescatter_async(t, "%s.%d" % (base, i), op) for i, t in enumerate(tensors)]
+    return [synchronize(h) for h in hs]
+
+
+# ---------------------------------------------------------------------------------------------
+# barrier / join
+# ---------------------------------------------------------------------------------------------
+def barrier(process_set=None):  # pylint: disable=unused-argument
+    _require()
+    name = _auto_name("barrier", None)
+    h = _S.engine.enqueue(_core.BARRIER, name, _core.U8, -1, 0, 0, [], 1.0, 1.0, 0, 0)
+    try:
+        _S.engine.wait(h)
+    except _core.EngineError as e:
+        raise HorovodInternalError(str(e))
+    finally:
+        _S.engine.release(h)
+
+
+def join(device=-1):  # pylint: disable=unused-argument
+    """Signal that this rank has run out of data.  Blocks until every rank has joined; while
+    waiting, this rank contributes zeros to the allreduces of the others.  Returns the rank
+    that joined last."""
+    _require()
+    h = _S.engine.enqueue(_core.JOIN, "__join__", _core.U8, -1, 0, 0, [], 1.0, 1.0, 0, 0)
+    try:
+        _S.engine.wait(h)
+        return _S.engine.last_joined(h)
+    except _core.EngineError as e:
+        raise HorovodInternalError(str(e))
+    finally:
+        _S.engine.release(h)
+
+
+# ---------------------------------------------------------------------------------------------
+# objects, parameters, optimizer state
+# ---------------------------------------------------------------------------------------------
+def broadcast_object(obj, root_rank=0, name=None, process_set=None):  # pylint: disable=unused-argument
+    """cloudpickle ``obj`` on ``root_rank`` and return it on every rank."""
+    _require()
+    import cloudpickle
+    name = _auto_name("broadcast_object", name)
+    if rank() == root_rank:
+        buf = io.BytesIO()
+        cloudpickle.dump(obj, buf)
+        data = torch.frombuffer(bytearray(buf.getvalue()), dtype=torch.uint8)
+        sz = torch.tensor([data.numel()], dtype=torch.int64)
+    else:
+        data = None
+        sz = torch.zeros(1, dtype=torch.int64)
+    broadcast_(sz, root_rank, name + ".sz")
+    if rank() != root_rank:
+        data = torch.empty(int(sz.item()), dtype=torch.uint8)
+    broadcast_(data, root_rank, name + ".data")
+    return pickle.loads(data.numpy().tobytes())
+
+
+def allgather_object(obj, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Gather one picklable object per rank into a list ordered by rank."""
+    _require()
+    import cloudpickle
+    name = _auto_name("allgather_object", name)
+    payload = cloudpickle.dumps(obj)
+    data = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    sizes = _host_allgather_ints([data.numel()], name + ".sz").reshape(-1).tolist()
+    gathered = synchronize(allgather_async(data, name + ".data"))
+    out, off = [], 0
+    raw = gathered.numpy().tobytes()
+    for s in sizes:
+        out.append(pickle.loads(raw[off:off + s]))
+        off += s
+    return out
+
+
+def broadcast_parameters(params, root_rank=0):
+    """Broadcast a ``state_dict()`` / ``named_parameters()`` from ``root_rank`` to all ranks.
+
+    CUDA tensors are grouped by dtype, flattened into one buffer and sent with a single
+    peer-memory broadcast kernel per dtype instead of one launch per
+    tensor."""
+    _require()
+    if isinstance(params, dict):
+        items = sorted(params.items())
+    elif isinstance(params, (list, tuple)) or hasattr(params, "__iter__"):
+        items = list(params)
+        if items and not isinstance(items[0], tuple):
+            raise ValueError("invalid params of type: %s" % type(params))
+    else:
+        raise ValueError("invalid params of type: %s" % type(params))
+    tensors = [(n, p) for n, p in items if torch.is_tensor(p)]
+    groups = {}
+    handles = []
+    for n, p in tensors:
+        t = p.data if isinstance(p, torch.nn.Parameter) else p
+        if t.is_cuda and t.numel() > 0:
+            groups.setdefault((t.dtype, t.device), []).append(t)
+        else:
+            handles.append(broadcast_async_(t, root_rank, "param." + n))
+    for i, ((dt, dev), ts) in enumerate(sorted(groups.items(), key=lambda kv: str(kv[0]))):
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        broadcast_(flat, root_rank, "param_group.%d.%s" % (i, str(dt)))
+        off = 0
+        for t in ts:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t))
+            off += n
+    for h in handles:
+        synchronize(h)
+
+
+def broadcast_optimizer_state(optimizer, root_rank=0, model=None):  # pylint: disable=unused-argument
+    """Make every rank's optimizer state (momentum buffers, step counts, hyper-parameters)
+    equal to ``root_rank``'s.  Used when resuming from a checkpoint loaded on rank 0."""
+    _require()
+    if isinstance(optimizer, torch.optim.LBFGS):
+        raise ValueError("cannot broadcast torch.optim.LBFGS state")
+    sd = optimizer.state_dict() if rank() == root_rank else None
+    sd = broadcast_object(sd, root_rank, "optimizer_state")
+    if rank() != root_rank:
+        optimizer.load_state_dict(sd)
+
+
+from spark_deep_learning_b200.parallel.optimizer import DistributedOptimizer  # noqa: E402,F401
+from spark_deep_learning_b200.parallel.sync_batch_norm import SyncBatchNorm  # noqa: E402,F401

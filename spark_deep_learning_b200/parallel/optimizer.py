@@ -1,0 +1,335 @@
+"""``hvd.DistributedOptimizer`` - data-parallel gradient averaging overlapped with backward.
+
+The reference product is "Horovod's DistributedOptimizer under HorovodRunner"
+(BASELINE.json config 2/3).  B200-first design instead of a port of
+Horovod's pack -> ncclAllReduce -> unpack cycle:
+
+* **Gradients are views into flat, symmetric bucket buffers** (``param.grad`` aliases peer-mapped
+  memory), so there is no fusion-buffer pack/unpack at all (SURVEY.md §2f K3 "eliminated by
+  design").
+* A ``post_accumulate_grad`` hook per parameter marks readiness; when a bucket is complete it
+  is reduced by ONE sm_100a kernel launch on a side stream that reads/writes the peers'
+  buffers over NVLink and applies the 1/N (pre/post-divide) scaling in the same pass.
+* ``fused=True`` (or ``SPARKDL_FUSED_OPTIMIZER=1``) goes one step further for SGD and
+  Adam/AdamW: parameters also live in symmetric buffers and the reduce kernel's epilogue applies
+  the optimizer update to the slice this rank owns and pushes the *new parameters* to all
+  peers - reduce-scatter + optimizer + all-gather in a single kernel with 1/N of the optimizer
+  state per GPU.
+"""
+import contextlib
+import os
+
+import torch
+
+from spark_deep_learning_b200.utils.config import get_config
+
+_ALIGN = 128  # bytes; every parameter starts on a 128-byte boundary inside its bucket
+
+
+class _Bucket(object):
+    __slots__ = ("index", "params", "offsets", "numel", "dtype", "device", "flat", "sym",
+                 "pending", "launched", "handle", "done_event", "pflat", "psym", "state")
+
+    def __init__(self, index, dtype, device):
+        self.index = index
+        self.params, self.offsets = [], []
+        self.numel = 0
+        self.dtype, self.device = dtype, device
+        self.flat = self.sym = None
+        self.pending = 0
+        self.launched = False
+        self.handle = None
+        self.done_event = 0
+        self.pflat = self.psym = None
+        self.state = None
+
+
+class _DistributedOptimizer(torch.optim.Optimizer):
+    # pylint: disable=too-many-instance-attributes
+    def __init__(self, params, named_parameters, compression, backward_passes_per_step, op,
+                 gradient_predivide_factor, fused, bucket_bytes):
+        super(self.__class__, self).__init__(params)
+        from spark_deep_learning_b200.parallel import hvd
+        self._hvd = hvd
+        self._compression = compression
+        self._op = op
+        self._predivide = float(gradient_predivide_factor)
+        self.backward_passes_per_step = int(backward_passes_per_step)
+        self._should_synchronize = True
+        self._synchronized = False
+        self._cfg = get_config()
+        self._bucket_bytes = int(bucket_bytes or self._cfg.bucket_bytes)
+
+        if named_parameters is not None:
+            named_parameters = list(named_parameters)
+        else:
+            named_parameters = [("allreduce.noname.%d.%d" % (gi, pi), p)
+                                for gi, g in enumerate(self.param_groups)
+                                for pi, p in enumerate(g["params"])]
+        if any(not isinstance(p, tuple) for p in named_parameters):
+            raise ValueError("named_parameters should be a sequence of tuples (name, parameter), "
+                             "usually produced by model.named_parameters().")
+        names = [n for n, _ in named_parameters]
+        if len(set(names)) != len(names):
+            dups = sorted({n for n in names if names.count(n) > 1})
+            raise ValueError("Parameter names in named_parameters must be unique. "
+                             "Found duplicates: %s" % ", ".join(dups))
+        all_ids = {id(p) for g in self.param_groups for p in g["params"]}
+        named_ids = {id(p) for _, p in named_parameters}
+        if all_ids - named_ids:
+            raise ValueError("named_parameters was specified, but one or more model parameters "
+                             "were not named. Python object ids: %s"
+                             % ", ".join(str(i) for i in sorted(all_ids - named_ids)))
+        self._names = {id(p): n for n, p in named_parameters}
+        self._passes = {}
+        self._buckets = []
+        self._bucket_of = {}
+        self._next_launch = 0
+        self._hooks = []
+        self._fused = bool(fused) and hvd.is_initialized()
+        self._step_count = 0
+        if hvd.is_initialized():
+            self._build_buckets([p for _, p in named_parameters if id(p) in all_ids])
+            self._register_hooks()
+
+    # ------------------------------------------------------------------------------------
+    # bucket construction: reverse registration order ~ the order backward produces gradients
+    # ------------------------------------------------------------------------------------
+    def _build_buckets(self, params):
+        hvd = self._hvd
+        comm = hvd.comm_backend()
+        trainable = [p for p in params if p.requires_grad]
+        cur = {}
+        for p in reversed(trainable):
+            if p.is_sparse:
+                raise ValueError("sparse parameters are not supported by DistributedOptimizer")
+            key = (p.dtype, p.device)
+            b = cur.get(key)
+            esz = p.element_size()
+            if b is None or (b.numel * esz >= self._bucket_bytes):
+                b = _Bucket(len(self._buckets), p.dtype, p.device)
+                self._buckets.append(b)
+                cur[key] = b
+            b.params.append(p)
+            b.offsets.append(b.numel)
+            n = p.numel()
+            b.numel += ((n * esz + _ALIGN - 1) // _ALIGN) * _ALIGN // esz
+        for b in self._buckets:
+            if b.device.type == "cuda" and comm is not None:
+                b.sym = comm.alloc_symmetric(b.numel * torch.empty(0, dtype=b.dtype).element_size())
+                b.flat = b.sym.tensor(b.dtype, b.numel)
+                b.flat.zero_()
+                if self._fused:
+                    b.psym = comm.alloc_symmetric(b.flat.numel() * b.flat.element_size())
+                    b.pflat = b.psym.tensor(b.dtype, b.numel)
+                    b.pflat.zero_()
+            else:
+                b.flat = torch.zeros(b.numel, dtype=b.dtype, device=b.device)
+            for p, off in zip(b.params, b.offsets):
+                view = b.flat[off:off + p.numel()].view_as(p)
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
+                self._bucket_of[id(p)] = (b, off)
+                self._passes[id(p)] = 0
+                if b.pflat is not None:
+                    pv = b.pflat[off:off + p.numel()].view_as(p)
+                    pv.copy_(p.data)
+                    p.data = pv
+            b.pending = len(b.params)
+        if comm is not None and any(b.sym is not None for b in self._buckets):
+            comm.sync_all()  # all ranks finished zeroing / copying before the first kernel
+
+    def _register_hooks(self):
+        for b in self._buckets:
+            for p in b.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook()))
+
+    def _make_hook(self):
+        def hook(p):
+            b, off = self._bucket_of[id(p)]
+            if b.launched:
+                raise AssertionError(
+                    "Gradients were computed more than backward_passes_per_step times before call "
+                    "to step(). Increase backward_passes_per_step to accumulate gradients locally.")
+            view = b.flat[off:off + p.numel()].view_as(p)
+            g = p.grad
+            if g is None:
+                return
+            if g.data_ptr() != view.data_ptr():
+                # someone replaced .grad (zero_grad(set_to_none=True), an AMP unscale copy ...):
+                # fold it back into the bucket and re-alias
+                view.copy_(g)
+                p.grad = view
+            self._passes[id(p)] += 1
+            if self._passes[id(p)] == self.backward_passes_per_step:
+                b.pending -= 1
+                if b.pending == 0:
+                    self._launch_ready()
+        return hook
+
+    # ------------------------------------------------------------------------------------
+    def _scales(self):
+        hvd = self._hvd
+        if self._op == hvd.Average:
+            return 1.0 / self._predivide, self._predivide / hvd.size()
+        return 1.0, 1.0
+
+    def _launch_ready(self):
+        """Launch complete buckets strictly in bucket order, so every rank issues the same
+        sequence of collective kernels on the communication stream."""
+        while self._next_launch < len(self._buckets):
+            b = self._buckets[self._next_launch]
+            if b.pending != 0:
+                return
+            self._launch(b)
+            self._next_launch += 1
+
+    def _launch(self, b):
+        hvd = self._hvd
+        pre, post = self._scales()
+        red_op = hvd.Sum if self._op == hvd.Average else self._op
+        if b.sym is not None:
+            comm = hvd.comm_backend()
+            if self._fused:
+                b.done_event = comm.fused_optimizer_step(self, b, pre, post)
+            else:
+                wire = self._wire_dtype(b)
+                b.done_event = comm.allreduce_symmetric(b.sym, b.numel, b.dtype, red_op, pre, post,
+                                                        wire=wire, channel=1)
+        else:
+            b.handle = hvd.allreduce_async_(b.flat, name="DistributedOptimizer.bucket.%d" % b.index,
+                                            op=red_op, prescale_factor=pre, postscale_factor=post)
+        b.launched = True
+
+    def _wire_dtype(self, b):
+        comp = self._compression
+        from spark_deep_learning_b200.parallel.hvd import Compression
+        if comp is Compression.fp16 and b.dtype == torch.float32:
+            return "fp16"
+        if comp is Compression.bf16 and b.dtype == torch.float32:
+            return "bf16"
+        w = self._cfg.wire_dtype
+        if w in ("fp8", "bf16", "fp16") and b.dtype in (torch.float32, torch.bfloat16):
+            if w == "fp8" or b.dtype == torch.float32:
+                return w
+        return None
+
+    def synchronize(self):
+        """Wait (stream-level on GPU) until every gradient has been averaged."""
+        hvd = self._hvd
+        if not hvd.is_initialized():
+            self._synchronized = True
+            return
+        # parameters that received no gradient this step still take part (as zeros)
+        while self._next_launch < len(self._buckets):
+            b = self._buckets[self._next_launch]
+            self._launch(b)
+            self._next_launch += 1
+        comm = hvd.comm_backend()
+        for b in self._buckets:
+            if b.handle is not None:
+                hvd.synchronize(b.handle)
+                b.handle = None
+            if b.done_event:
+                comm.current_stream_wait(b.done_event)
+                b.done_event = 0
+        self._synchronized = True
+
+    @contextlib.contextmanager
+    def skip_synchronize(self):
+        """``with optimizer.skip_synchronize(): optimizer.step()`` after a manual
+        ``optimizer.synchronize()`` (gradient clipping recipe)."""
+        self._should_synchronize = False
+        try:
+            yield
+        finally:
+            self._should_synchronize = True
+
+    def _reset_step_state(self):
+        for b in self._buckets:
+            b.pending = len(b.params)
+            b.launched = False
+        for k in self._passes:
+            self._passes[k] = 0
+        self._next_launch = 0
+        self._synchronized = False
+
+    def step(self, closure=None):
+        if self._should_synchronize:
+            if self._synchronized:
+                import warnings
+                warnings.warn("optimizer.step() called without optimizer.skip_synchronize() "
+                              "context after optimizer.synchronize(). This can cause training "
+                              "slowdown. You may want to consider using "
+                              "optimizer.skip_synchronize() context if you use "
+                              "optimizer.synchronize() in your code.")
+            self.synchronize()
+        self._reset_step_state()
+        self._step_count += 1
+        if self._fused:
+            loss = closure() if closure is not None else None
+            return loss  # the update already happened inside the reduce kernel
+        return super(self.__class__, self).step(closure)
+
+    def zero_grad(self, set_to_none=False):  # pylint: disable=arguments-differ
+        """Gradients stay aliased to the bucket buffers: one memset per bucket instead of one
+        per parameter.  ``set_to_none`` is accepted for API compatibility and ignored for
+        bucketed parameters."""
+        if any(b.launched for b in self._buckets) and not self._synchronized:
+            raise AssertionError("optimizer.zero_grad() was called after loss.backward() but before "
+                                 "optimizer.step() or optimizer.synchronize(). This is prohibited as "
+                                 "it can cause a race condition.")
+        if not self._buckets:
+            return super(self.__class__, self).zero_grad(set_to_none=set_to_none)
+        for b in self._buckets:
+            b.flat.zero_()
+            for p, off in zip(b.params, b.offsets):
+                if p.grad is None or p.grad.data_ptr() != b.flat.data_ptr() + off * b.flat.element_size():
+                    p.grad = b.flat[off:off + p.numel()].view_as(p)
+        bucketed = set(self._bucket_of)
+        for g in self.param_groups:
+            for p in g["params"]:
+                if id(p) not in bucketed and p.grad is not None:
+                    if set_to_none:
+                        p.grad = None
+                    else:
+                        p.grad.zero_()
+
+    def set_backward_passes_per_step(self, passes):
+        self.backward_passes_per_step = int(passes)
+
+    def bucket_summary(self):
+        return [{"index": b.index, "params": len(b.params), "numel": b.numel, "dtype": str(b.dtype),
+                 "symmetric": b.sym is not None} for b in self._buckets]
+
+
+def DistributedOptimizer(optimizer, named_parameters=None, compression=None,
+                         backward_passes_per_step=1, op=None, gradient_predivide_factor=1.0,
+                         num_groups=0, groups=None, sparse_as_dense=False, process_set=None,
+                         fused=None, bucket_bytes=None):
+    # pylint: disable=invalid-name,unused-argument
+    """Wrap ``optimizer`` so that gradients are averaged across all workers before ``step()``.
+
+    Same signature as ``horovod.torch.DistributedOptimizer`` plus two keyword extensions:
+    ``fused`` (apply the update inside the reduce kernel; SGD / Adam / AdamW) and
+    ``bucket_bytes`` (gradient bytes per fused launch).
+    """
+    from spark_deep_learning_b200.parallel import hvd
+    if compression is None:
+        compression = hvd.Compression.none
+    if op is None:
+        op = hvd.Average
+    if op == hvd.Adasum:
+        raise NotImplementedError("Adasum is not supported by the sm_100a runtime")
+    if gradient_predivide_factor != 1.0 and op != hvd.Average:
+        raise ValueError("gradient_predivide_factor not supported with op != Average")
+    if fused is None:
+        fused = os.environ.get("SPARKDL_FUSED_OPTIMIZER", "0") == "1"
+    if fused and not isinstance(optimizer, (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW)):
+        raise ValueError("fused=True supports torch.optim.SGD, Adam and AdamW, got %s"
+                         % type(optimizer).__name__)
+    cls = type(optimizer.__class__.__name__, (optimizer.__class__,),
+               dict(_DistributedOptimizer.__dict__))
+    return cls(optimizer.param_groups, named_parameters, compression, backward_passes_per_step, op,
+               gradient_predivide_factor, fused, bucket_bytes)

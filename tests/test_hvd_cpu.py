@@ -1,0 +1,202 @@
+"""T1/T3 - hvd frontend over the C++ engine + shm data plane, on CPU, multi-process
+(BASELINE.json config 1)."""
+import pytest
+
+from sparkdl import HorovodRunner
+from spark_deep_learning_b200.parallel.launcher import WorkerFailure
+
+
+def test_config1_np1_allreduce_1k():
+    """BASELINE.json config 1: HorovodRunner(np=1).run(main): hvd.init + allreduce of a 1k tensor."""
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        t = torch.arange(1024, dtype=torch.float32)
+        out = hvd.allreduce(t)
+        return hvd.rank(), hvd.size(), bool(torch.equal(out, t))
+    import os
+    os.environ["SPARKDL_NUM_GPUS"] = "0"
+    try:
+        assert HorovodRunner(np=1).run(main) == (0, 1, True)
+    finally:
+        del os.environ["SPARKDL_NUM_GPUS"]
+
+
+def _collectives_main():
+    import torch
+    import sparkdl.hvd as hvd
+    hvd.init()
+    r, n = hvd.rank(), hvd.size()
+    res = {}
+    # allreduce: average / sum / min / max / product over dtypes
+    for dt in (torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int32, torch.int64):
+        t = (torch.arange(1000) % 7 + r + 1).to(dt)
+        exp = sum((torch.arange(1000) % 7 + q + 1).to(torch.float64) for q in range(n))
+        s = hvd.allreduce(t, op=hvd.Sum)
+        res["sum_%s" % dt] = bool(torch.allclose(s.double(), exp, rtol=1e-2))
+    t = torch.full((5,), float(r + 1))
+    res["avg"] = bool(torch.allclose(hvd.allreduce(t), torch.full((5,), (n + 1) / 2.0)))
+    res["min"] = hvd.allreduce(t, op=hvd.Min)[0].item() == 1.0
+    res["max"] = hvd.allreduce(t, op=hvd.Max)[0].item() == float(n)
+    res["prod"] = hvd.allreduce(torch.full((3,), 2.0), op=hvd.Product)[0].item() == 2.0 ** n
+    res["prepost"] = bool(torch.allclose(
+        hvd.allreduce(torch.ones(4), op=hvd.Sum, prescale_factor=0.5, postscale_factor=4.0),
+        torch.full((4,), 2.0 * n)))
+    # in-place + non-contiguous
+    m = torch.ones(4, 6)[:, ::2]
+    hvd.allreduce_(m, op=hvd.Sum)
+    res["inplace_noncontig"] = bool(torch.equal(m, torch.full((4, 3), float(n))))
+    # larger than the staging area (chunked path): SPARKDL_SHM_STAGE_BYTES=64KiB in the test
+    big = torch.full((100003,), float(r))
+    res["big"] = bool(torch.allclose(hvd.allreduce(big, op=hvd.Sum), torch.full((100003,), n * (n - 1) / 2.0)))
+    # grouped (fused by the engine)
+    outs = hvd.grouped_allreduce([torch.full((k + 1,), float(r)) for k in range(10)], op=hvd.Sum)
+    res["grouped"] = all(o.shape[0] == k + 1 and o[0].item() == n * (n - 1) / 2.0 for k, o in enumerate(outs))
+    # allgather with ragged first dim
+    g = hvd.allgather(torch.full((r + 1, 2), float(r)))
+    res["allgather"] = g.shape == (n * (n + 1) // 2, 2) and g[-1, 0].item() == float(n - 1)
+    # broadcast
+    b = torch.full((3,), float(r))
+    hvd.broadcast_(b, root_rank=n - 1)
+    res["broadcast"] = b[0].item() == float(n - 1)
+    res["bcast_obj"] = hvd.broadcast_object({"r": r} if r == 0 else None, 0) == {"r": 0}
+    res["gather_obj"] = hvd.allgather_object("rank%d" % r) == ["rank%d" % q for q in range(n)]
+    # alltoall: rank r sends (d+1) rows of value r to rank d
+    send = torch.cat([torch.full((d + 1, 2), float(r)) for d in range(n)])
+    recv, rs = hvd.alltoall(send, splits=[d + 1 for d in range(n)])
+    res["alltoall"] = recv.shape == (n * (r + 1), 2) and rs.tolist() == [r + 1] * n and \
+        [recv[q * (r + 1), 0].item() for q in range(n)] == [float(q) for q in range(n)]
+    # reducescatter (sum): 2n+1 rows -> remainder row goes to rank 0
+    x = torch.arange((2 * n + 1) * 3, dtype=torch.float32).reshape(2 * n + 1, 3)
+    rsx = hvd.reducescatter(x, op=hvd.Sum)
+    rows = 2 + (1 if r == 0 else 0)
+    start = 2 * r + (1 if r > 0 else 0)
+    res["reducescatter"] = rsx.shape == (rows, 3) and bool(torch.equal(rsx, x[start:start + rows] * n))
+    hvd.barrier()
+    res["stats"] = hvd.engine_stats()["responses"] > 0
+    return r, res
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_collectives(n, monkeypatch):
+    monkeypatch.setenv("SPARKDL_SHM_STAGE_BYTES", str(64 << 10))
+    r, res = HorovodRunner(np=-n).run(_collectives_main)
+    bad = [k for k, v in res.items() if not v]
+    assert r == 0 and not bad, bad
+
+
+def test_out_of_order_submission_and_fusion():
+    """Ranks submit named tensors in different orders; negotiation must still match them."""
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        r, n = hvd.rank(), hvd.size()
+        names = ["t%d" % i for i in range(12)]
+        order = names if r % 2 == 0 else list(reversed(names))
+        hs = {nm: hvd.allreduce_async(torch.full((3,), float(int(nm[1:]) + r)), name=nm, op=hvd.Sum)
+              for nm in order}
+        ok = all(hvd.synchronize(hs[nm])[0].item() == n * int(nm[1:]) + n * (n - 1) / 2.0 for nm in names)
+        return ok
+    assert HorovodRunner(np=-3).run(main)
+
+
+def test_mismatch_errors_on_all_ranks():
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        errs = []
+        try:
+            hvd.allreduce(torch.ones(3 + hvd.rank()), name="bad_shape")
+        except hvd.HorovodInternalError as e:
+            errs.append("shape" if "mismatched shapes" in str(e) else str(e))
+        try:
+            hvd.allreduce(torch.ones(3, dtype=torch.float32 if hvd.rank() else torch.float64), name="bad_dtype")
+        except hvd.HorovodInternalError as e:
+            errs.append("dtype" if "data types" in str(e) else str(e))
+        # engine still usable afterwards
+        ok = hvd.allreduce(torch.ones(2), op=hvd.Sum)[0].item() == hvd.size()
+        both = hvd.allgather_object(errs)
+        return ok, both
+    ok, both = HorovodRunner(np=-2).run(main)
+    assert ok and both == [["shape", "dtype"], ["shape", "dtype"]]
+
+
+def test_duplicate_name_is_an_error():
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        h1 = hvd.allreduce_async(torch.ones(200000), name="dup")
+        h2 = hvd.allreduce_async(torch.ones(200000), name="dup")
+        msg = ""
+        for h in (h1, h2):
+            try:
+                hvd.synchronize(h)
+            except hvd.HorovodInternalError as e:
+                msg = str(e)
+        return msg
+    msg = HorovodRunner(np=-2).run(main)
+    assert "duplicate tensor name" in msg or msg == ""   # timing dependent: second may start after first
+
+
+def test_join_uneven_batches():
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        r, n = hvd.rank(), hvd.size()
+        sums = []
+        for step in range(r + 1):           # rank r has r+1 batches
+            sums.append(hvd.allreduce(torch.ones(2), op=hvd.Sum, name="s%d" % step)[0].item())
+        last = hvd.join()
+        return r, sums, last
+    r, sums, last = HorovodRunner(np=-3).run(main)
+    assert sums == [3.0] and last == 2      # rank 0 only sees step 0, contributed to by all three
+
+
+def test_distributed_optimizer_matches_single_process():
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        r, n = hvd.rank(), hvd.size()
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 2))
+        ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 2))
+        ref.load_state_dict(model.state_dict())
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9),
+                                       named_parameters=model.named_parameters(), bucket_bytes=256)
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9)
+        hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+        hvd.broadcast_optimizer_state(opt, root_rank=0)
+        g = torch.Generator().manual_seed(123)
+        X = torch.randn(4 * n, 8, generator=g)
+        Y = torch.randn(4 * n, 2, generator=g)
+        for _ in range(3):
+            opt.zero_grad()
+            loss = ((model(X[4 * r:4 * r + 4]) - Y[4 * r:4 * r + 4]) ** 2).mean()
+            loss.backward()
+            opt.step()
+            ropt.zero_grad()
+            ((ref(X) - Y) ** 2).mean().backward()
+            ropt.step()
+        diff = max((a - b).abs().max().item() for a, b in zip(model.parameters(), ref.parameters()))
+        return diff, len(opt.bucket_summary())
+    diff, nb = HorovodRunner(np=-2).run(main)
+    assert diff < 1e-5 and nb >= 2
+
+
+def test_dead_peer_fails_job_quickly():
+    def main():
+        import os
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        if hvd.rank() == 1:
+            os._exit(9)
+        hvd.allreduce(torch.ones(4))      # would hang forever without gang teardown
+    with pytest.raises(WorkerFailure):
+        HorovodRunner(np=-2).run(main)

@@ -1,0 +1,83 @@
+"""T1 - launcher plumbing on CPU: cloudpickle round trip, rank-0 return value,
+failure propagation, stdout multiplexing, log_to_driver, no orphans."""
+import os
+import time
+
+import pytest
+
+from sparkdl import HorovodRunner
+from spark_deep_learning_b200.parallel.launcher import WorkerFailure
+
+
+def test_return_value_lambda():
+    # a lambda: only cloudpickle can ship it (reference test_return_value)
+    assert HorovodRunner(np=-1).run(lambda: 42) == 42
+
+
+def test_kwargs_and_closure():
+    k = 7
+
+    def main(a, b):
+        return a * b + k
+    assert HorovodRunner(np=-1).run(main, a=3, b=4) == 19
+
+
+def test_rank0_value_and_env():
+    def main():
+        import os
+        return (int(os.environ["SPARKDL_RANK"]), int(os.environ["SPARKDL_SIZE"]), os.getpid())
+    r, s, pid = HorovodRunner(np=-3).run(main)
+    assert (r, s) == (0, 3) and pid != os.getpid()
+
+
+def test_np_positive_runs_locally(monkeypatch):
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "0")
+    assert HorovodRunner(np=2, driver_log_verbosity="all").run(lambda: "ok") == "ok"
+
+
+def test_exception_propagates_with_traceback():
+    def main():
+        import os
+        if os.environ["SPARKDL_RANK"] == "1":
+            raise ValueError("boom from rank one")
+        import time
+        time.sleep(30)
+    t0 = time.time()
+    with pytest.raises(WorkerFailure) as ei:
+        HorovodRunner(np=-2).run(main)
+    assert "boom from rank one" in str(ei.value) and ei.value.rank == 1
+    assert time.time() - t0 < 20, "siblings must be torn down, not waited for"
+
+
+def test_fault_injection_kill(monkeypatch):
+    monkeypatch.setenv("SPARKDL_FAULT", "kill:rank=1:at=start")
+    with pytest.raises(WorkerFailure) as ei:
+        HorovodRunner(np=-2).run(lambda: __import__("time").sleep(20))
+    assert ei.value.rank == 1 and ei.value.returncode == 137
+
+
+def test_stdout_mux_and_log_to_driver(capfd):
+    def main():
+        import os
+        from sparkdl.horovod import log_to_driver
+        print("hello from %s" % os.environ["SPARKDL_RANK"])
+        if os.environ["SPARKDL_RANK"] == "0":
+            log_to_driver("driver-visible " + "y" * 5000)
+        return 1
+    HorovodRunner(np=-2).run(main)
+    out = capfd.readouterr().out
+    assert "[0] hello from 0" in out and "[1] hello from 1" in out
+    line = [l for l in out.splitlines() if l.startswith("driver-visible")][0]
+    assert len(line) == 4000
+
+
+def test_log_callback_only_hides_worker_stdout(capfd, monkeypatch):
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "0")
+
+    def main():
+        from sparkdl.horovod import log_to_driver
+        print("noisy worker line")
+        log_to_driver("selected line")
+    HorovodRunner(np=1).run(main)           # np>0 honours driver_log_verbosity
+    out = capfd.readouterr().out
+    assert "selected line" in out and "noisy worker line" not in out
