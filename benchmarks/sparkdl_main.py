@@ -1,0 +1,102 @@
+"""The training function run by OUR arm of bench.py - the code a user of this framework writes.
+
+Public API only: ``sparkdl.hvd`` (init / broadcast_parameters / DistributedOptimizer) and the
+model zoo.  Gradient averaging + optimizer update run in the fused sm_100a peer-memory kernels.
+"""
+
+
+def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, seq_len=128,
+          fused_optimizer=True, fused_model=True, wire=None):
+    import os
+    import time
+
+    import torch
+
+    import sparkdl.hvd as hvd
+    from spark_deep_learning_b200 import models
+
+    if wire:
+        os.environ["SPARKDL_WIRE_DTYPE"] = wire
+    hvd.init()
+    rank, world = hvd.rank(), hvd.size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(1234)
+    torch.backends.cudnn.benchmark = True
+    comm = hvd.comm_backend()
+
+    if model_name == "resnet50":
+        model = models.resnet50(fused=fused_model).to(dev).to(memory_format=torch.channels_last)
+        base = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        host_x = torch.randn(batch, 3, 224, 224).pin_memory()
+        host_y = torch.randint(0, 1000, (batch,)).pin_memory()
+    else:
+        model = models.bert_large(fused=fused_model).to(dev)
+        base = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+        host_x = torch.randint(0, 30522, (batch, seq_len)).pin_memory()
+        host_y = torch.randint(0, 30522, (batch, seq_len)).pin_memory()
+    opt = hvd.DistributedOptimizer(base, named_parameters=model.named_parameters(), fused=fused_optimizer)
+    hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+    crit = torch.nn.CrossEntropyLoss()
+
+    def fwd(x, y):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if model_name == "resnet50":
+                return crit(model(x.contiguous(memory_format=torch.channels_last)), y)
+            return model(x, labels=y)
+
+    dx, dy = host_x.to(dev), host_y.to(dev)
+
+    def step(x, y):
+        opt.zero_grad()
+        loss = fwd(x, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        hvd.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step(dx, dy)
+    barrier()
+    from spark_deep_learning_b200.utils import launch_counter
+    l0 = launch_counter.total(comm)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step(dx, dy)
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = launch_counter.total(comm) - l0
+
+    k = e2e_steps or steps
+    for _ in range(2):
+        step(host_x.to(dev, non_blocking=True), host_y.to(dev, non_blocking=True)).item()
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(k):
+        x = host_x.to(dev, non_blocking=True)
+        y = host_y.to(dev, non_blocking=True)
+        loss_val = step(x, y).item()
+    e3.record()
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = e2.elapsed_time(e3)
+    if comm is not None:
+        comm.check_error()
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64)
+    t = hvd.allreduce(t, op=hvd.Max)
+    res = {"dev_ms": t[0].item(), "e2e_ms": t[1].item(), "steps": steps, "e2e_steps": k,
+           "h2d_bytes": host_x.numel() * host_x.element_size() + host_y.numel() * host_y.element_size(),
+           "d2h_bytes": 4, "e2e_wall_ms": e2e_wall_ms, "loss": loss_val, "world": world, "batch": batch,
+           "gpu_launches": int(launches),
+           "transport": getattr(comm, "transport", None), "multicast": getattr(comm, "multicast", None),
+           "buckets": len(opt.bucket_summary())}
+    hvd.shutdown()
+    return res

@@ -625,7 +625,20 @@ void Engine::execute(const Response& r) {
     case kAlltoall: {
       Entry* e = es[0];
       if (!e) { err = "internal: alltoall response without a local entry"; break; }
-      if (r.device >= 0) { complete(e, "CUDA alltoall goes through the symmetric-memory frontend"); return; }
+      if (r.device >= 0) {
+        if (!gpu_fn_) { complete(e, "CUDA tensor submitted but no GPU executor is registered"); return; }
+        GpuWork w;
+        memset(&w, 0, sizeof(w));
+        w.type = r.type; w.dtype = r.dtype; w.device = r.device; w.n = 1;
+        w.in = &e->in; w.out = &e->out; w.numel = &e->numel; w.ready_events = &e->ready_event;
+        w.row_elems = r.row_elems; w.splits = r.splits; w.splits_stride = world;
+        char eb[512] = {0};
+        uint64_t ev = 0;
+        int rc = gpu_fn_(gpu_ctx_, &w, &ev, eb, sizeof(eb));
+        if (auto st = state(e->handle)) st->done_event = ev;
+        complete(e, rc == 0 ? "" : eb);
+        return;
+      }
       auto st = state(e->handle);
       std::vector<int64_t> m((size_t)world * world);
       int64_t recv_rows = 0;
@@ -646,7 +659,24 @@ void Engine::execute(const Response& r) {
     case kReducescatter: {
       Entry* e = es[0];
       if (!e) { err = "internal: reducescatter response without a local entry"; break; }
-      if (r.device >= 0) { complete(e, "CUDA reducescatter goes through the symmetric-memory frontend"); return; }
+      if (r.device >= 0) {
+        if (!gpu_fn_) { complete(e, "CUDA tensor submitted but no GPU executor is registered"); return; }
+        GpuWork w;
+        memset(&w, 0, sizeof(w));
+        w.type = r.type; w.dtype = r.dtype; w.device = r.device; w.n = 1;
+        w.op = r.op == kAverage ? (uint32_t)kSum : r.op;
+        w.prescale = r.prescale; w.postscale = r.postscale;
+        w.in = &e->in; w.out = &e->out; w.numel = &e->numel; w.ready_events = &e->ready_event;
+        int64_t d0v = e->req.ndim > 0 ? e->req.shape[0] : 1;
+        w.dim0 = &d0v;
+        w.row_elems = d0v > 0 ? e->numel / d0v : 0;
+        char eb[512] = {0};
+        uint64_t ev = 0;
+        int rc = gpu_fn_(gpu_ctx_, &w, &ev, eb, sizeof(eb));
+        if (auto st = state(e->handle)) st->done_event = ev;
+        complete(e, rc == 0 ? "" : eb);
+        return;
+      }
       auto st = state(e->handle);
       const int64_t d0 = e->req.ndim > 0 ? e->req.shape[0] : 1;
       const int64_t row = d0 > 0 ? e->numel / d0 : 0;

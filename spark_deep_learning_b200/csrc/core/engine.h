@@ -16,25 +16,10 @@
 
 #include "common.h"
 #include "cpu_collectives.h"
+#include "gpu_work.h"
 #include "shm.h"
 
 namespace sdl {
-
-// Work item handed to the CUDA executor (lives in libsparkdl_cuda.so).
-struct GpuWork {
-  uint32_t type, dtype, op;
-  int32_t root, device;
-  uint32_t n;
-  double prescale, postscale;
-  void** in;
-  void** out;
-  int64_t* numel;
-  uint64_t* ready_events;     // cudaEvent_t recorded by the producer stream (0 = none)
-  const int64_t* dim0;        // allgather: rows per rank
-  int64_t row_elems;
-  const int32_t* splits;      // alltoall matrix [src * world + dst] in rows
-};
-typedef int (*GpuExecFn)(void* ctx, const GpuWork* work, uint64_t* done_event, char* err, int errlen);
 
 struct EngineOptions {
   std::string shm_name;

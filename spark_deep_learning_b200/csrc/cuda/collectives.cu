@@ -1,0 +1,684 @@
+// sm_100a peer-memory collectives: every op is ONE kernel that synchronises with its peers
+// through flag words in peer memory and moves data with P2P loads/stores or NVLS multimem
+// instructions over NVSwitch.  No NCCL anywhere.  Inventory: SURVEY.md §2f K1 (one-shot),
+// K2 (two-shot P2P + NVLS), K3 (pack/unpack), K4 (allgather), K5 (broadcast), K6/K7 (16-bit and
+// block-scaled fp8 wire formats), K9 (barrier), K10 (reducescatter / alltoall).
+#include <cstdio>
+#include <cstring>
+
+#include "comm.h"
+
+namespace sdlc {
+
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// =====================================================================================================
+// K9  barrier only
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads) barrier_kernel(CollCtx c) {
+  EpochScope ep(c);
+  coll_barrier(c, ep.base + 1);
+  ep.commit(c, 1);
+}
+
+// shared reduction step: v[p] holds the 16-byte vector of rank p, fixed summation order 0..W-1 so
+// every rank computes bit-identical results
+template <typename T>
+__device__ __forceinline__ uint4 reduce_vectors(const uint4* v, int world, int op, float pre, float post) {
+  using Tr = VecTraits<T>;
+  typename Tr::Acc acc[Tr::N], t[Tr::N];
+  vec_unpack<T>(v[0], acc);
+#pragma unroll
+  for (int i = 0; i < Tr::N; ++i) acc[i] = scale_val(acc[i], pre);
+#pragma unroll
+  for (int p = 1; p < kMaxPeers; ++p) {
+    if (p < world) {
+      vec_unpack<T>(v[p], t);
+#pragma unroll
+      for (int i = 0; i < Tr::N; ++i) acc[i] = reduce_op(acc[i], scale_val(t[i], pre), op);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < Tr::N; ++i) acc[i] = scale_val(acc[i], post);
+  return vec_pack<T>(acc);
+}
+
+// =====================================================================================================
+// K1  one-shot allreduce, in place, latency regime.  Every rank reads all peers and keeps the
+// result in registers across the second barrier, then overwrites its own buffer.
+// =====================================================================================================
+constexpr int kOneShotR = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+allreduce_oneshot_kernel(CollCtx c, long long nvec, int op, float pre, float post) {
+  EpochScope ep(c);
+  coll_barrier(c, ep.base + 1);
+  uint4 res[kOneShotR];
+  const int world = c.world;
+#pragma unroll
+  for (int r = 0; r < kOneShotR; ++r) {
+    const long long idx = ((long long)r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx < nvec) {
+      uint4 v[kMaxPeers];
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < world) v[p] = ld_peer_v4(static_cast<const uint4*>(c.data.p[p]) + idx);
+      res[r] = reduce_vectors<T>(v, world, op, pre, post);
+    }
+  }
+  coll_barrier(c, ep.base + 2);  // all peers have finished reading this block's region
+  uint4* mine = static_cast<uint4*>(c.data.p[c.rank]);
+#pragma unroll
+  for (int r = 0; r < kOneShotR; ++r) {
+    const long long idx = ((long long)r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx < nvec) mine[idx] = res[r];
+  }
+  ep.commit(c, 2);
+}
+
+// =====================================================================================================
+// K2  two-shot allreduce over P2P, in place: rank r reduces slice r from all peers and pushes the
+// result straight into every peer's buffer (reduce-scatter and all-gather in one pass).
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+allreduce_twoshot_kernel(CollCtx c, long long nvec, int op, float pre, float post) {
+  EpochScope ep(c);
+  coll_barrier(c, ep.base + 1);
+  const int world = c.world;
+  const long long per = ceil_div_ll(nvec, world);
+  const long long lo = min(nvec, (long long)c.rank * per), hi = min(nvec, lo + per);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool has1 = i1 < hi;
+    uint4 a[kMaxPeers], b[kMaxPeers];
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < world) a[p] = ld_peer_v4(static_cast<const uint4*>(c.data.p[p]) + i0);
+    if (has1) {
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < world) b[p] = ld_peer_v4(static_cast<const uint4*>(c.data.p[p]) + i1);
+    }
+    const uint4 ra = reduce_vectors<T>(a, world, op, pre, post);
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < world) st_peer_v4(static_cast<uint4*>(c.data.p[p]) + i0, ra);
+    if (has1) {
+      const uint4 rb = reduce_vectors<T>(b, world, op, pre, post);
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < world) st_peer_v4(static_cast<uint4*>(c.data.p[p]) + i1, rb);
+    }
+  }
+  coll_barrier(c, ep.base + 2);
+  ep.commit(c, 2);
+}
+
+// =====================================================================================================
+// K2  two-shot allreduce over NVLS: multimem.ld_reduce lets the switch sum the N copies, the fused
+// scale runs in registers, multimem.st replicates the result to every GPU.  Sum only.
+// =====================================================================================================
+template <typename T> __device__ __forceinline__ uint4 mc_ld_reduce(const void* p);
+template <> __device__ __forceinline__ uint4 mc_ld_reduce<float>(const void* p) { return mc_ld_reduce_f32(p); }
+template <> __device__ __forceinline__ uint4 mc_ld_reduce<__nv_bfloat16>(const void* p) { return mc_ld_reduce_bf16(p); }
+template <> __device__ __forceinline__ uint4 mc_ld_reduce<__half>(const void* p) { return mc_ld_reduce_f16(p); }
+
+template <typename T>
+__device__ __forceinline__ uint4 scale_vector(const uint4& v, float s) {
+  using Tr = VecTraits<T>;
+  typename Tr::Acc a[Tr::N];
+  vec_unpack<T>(v, a);
+#pragma unroll
+  for (int i = 0; i < Tr::N; ++i) a[i] = scale_val(a[i], s);
+  return vec_pack<T>(a);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+allreduce_multimem_kernel(CollCtx c, long long nvec, float scale) {
+  EpochScope ep(c);
+  coll_barrier(c, ep.base + 1);
+  const long long per = ceil_div_ll(nvec, c.world);
+  const long long lo = min(nvec, (long long)c.rank * per), hi = min(nvec, lo + per);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  uint4* mc = static_cast<uint4*>(c.mc);
+  const bool do_scale = scale != 1.0f;
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < hi) v[u] = mc_ld_reduce<T>(mc + i0 + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < hi) mc_st_v4(mc + i0 + u * stride, do_scale ? scale_vector<T>(v[u], scale) : v[u]);
+  }
+  coll_barrier(c, ep.base + 2);
+  ep.commit(c, 2);
+}
+
+// =====================================================================================================
+// K6/K7  wire-format allreduce: storage dtype (fp32 / bf16) stays local, what crosses NVLink is a
+// 16-bit cast or block-scaled fp8 (e4m3 payload + one fp32 scale per 128 elements), accumulated in
+// fp32.  Quantise -> barrier -> reduce slice + requantise + push -> barrier -> dequantise: one kernel.
+// =====================================================================================================
+constexpr int kUnit = 128;  // elements per scale block; one warp handles one unit, 4 elements per lane
+
+template <typename S> __device__ __forceinline__ void load4(const S* p, float* f);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float* f) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  bf16x2_to_f(v.x, f[0], f[1]); bf16x2_to_f(v.y, f[2], f[3]);
+}
+template <typename S> __device__ __forceinline__ void store4(S* p, const float* f);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(f_to_bf16x2(f[0], f[1]), f_to_bf16x2(f[2], f[3]));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t quant_fp8x4(const float* f, float inv) {
+  const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[0] * inv, f[1] * inv), __NV_SATFINITE, __NV_E4M3);
+  const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[2] * inv, f[3] * inv), __NV_SATFINITE, __NV_E4M3);
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+__device__ __forceinline__ void dequant_fp8x4(uint32_t q, float s, float* f) {
+  const __half2_raw a = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(q & 0xffff), __NV_E4M3);
+  const __half2_raw b = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(q >> 16), __NV_E4M3);
+  const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a));
+  const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&b));
+  f[0] = fa.x * s; f[1] = fa.y * s; f[2] = fb.x * s; f[3] = fb.y * s;
+}
+
+// wire layouts: 16-bit: unit u at byte u*256, lane l at +8l.  fp8: payload unit u at byte u*128 (+4l),
+// scales at byte n_units*128 + 4u.
+template <int WIRE>
+__device__ __forceinline__ void wire_store(char* base, long long n_units, long long u, int lane, const float* f, bool remote) {
+  if (WIRE == kWireFP8) {
+    float amax = fmaxf(fmaxf(fabsf(f[0]), fabsf(f[1])), fmaxf(fabsf(f[2]), fabsf(f[3])));
+    amax = warp_max(amax);
+    const float s = amax > 0.f ? amax * (1.0f / 448.0f) : 1.0f;
+    const uint32_t q = quant_fp8x4(f, 1.0f / s);
+    if (remote) {
+      st_peer_u32(base + u * kUnit + lane * 4, q);
+      if (lane == 0) st_peer_u32(base + n_units * kUnit + u * 4, __float_as_uint(s));
+    } else {
+      *reinterpret_cast<uint32_t*>(base + u * kUnit + lane * 4) = q;
+      if (lane == 0) *reinterpret_cast<float*>(base + n_units * kUnit + u * 4) = s;
+    }
+  } else {
+    uint2 q;
+    if (WIRE == kWireBF16) q = make_uint2(f_to_bf16x2(f[0], f[1]), f_to_bf16x2(f[2], f[3]));
+    else q = make_uint2(f_to_f16x2(f[0], f[1]), f_to_f16x2(f[2], f[3]));
+    if (remote) st_peer_v2(base + u * (kUnit * 2) + lane * 8, q);
+    else *reinterpret_cast<uint2*>(base + u * (kUnit * 2) + lane * 8) = q;
+  }
+}
+
+template <int WIRE>
+__device__ __forceinline__ void wire_load(const char* base, long long n_units, long long u, int lane, float* f) {
+  if (WIRE == kWireFP8) {
+    const uint32_t q = ld_peer_u32(base + u * kUnit + lane * 4);
+    const float s = __uint_as_float(ld_peer_u32(base + n_units * kUnit + u * 4));
+    dequant_fp8x4(q, s, f);
+  } else {
+    const uint2 q = ld_peer_v2(base + u * (kUnit * 2) + lane * 8);
+    if (WIRE == kWireBF16) { bf16x2_to_f(q.x, f[0], f[1]); bf16x2_to_f(q.y, f[2], f[3]); }
+    else { f16x2_to_f(q.x, f[0], f[1]); f16x2_to_f(q.y, f[2], f[3]); }
+  }
+}
+
+template <typename S, int WIRE>
+__global__ void __launch_bounds__(kThreads)
+allreduce_wire_kernel(CollCtx c, S* storage, long long n, float pre, float post) {
+  EpochScope ep(c);
+  const int world = c.world, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const long long n_units = ceil_div_ll(n, kUnit);
+  const long long upr = ceil_div_ll(n_units, world);
+  char* my_wire = static_cast<char*>(c.data.p[c.rank]);
+  // phase 0: quantise my gradients into my wire buffer.  Block b owns the units j (within every
+  // slice) with j % gridDim.x == b - exactly the units block b of the slice owner will read.
+  for (int s = 0; s < world; ++s) {
+    const long long s_lo = min(n_units, (long long)s * upr), s_len = min(n_units, s_lo + upr) - s_lo;
+    for (long long j = blockIdx.x + (long long)gridDim.x * warp; j < s_len; j += (long long)gridDim.x * wpb) {
+      const long long u = s_lo + j, e = u * kUnit + lane * 4;
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      if (e < n) {
+        load4<S>(storage + e, f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] *= pre;
+      }
+      wire_store<WIRE>(my_wire, n_units, u, lane, f, false);
+    }
+  }
+  coll_barrier(c, ep.base + 1);
+  // phase 1: reduce my slice over all peers (fp32), requantise, push to every peer's wire buffer
+  {
+    const long long s_lo = min(n_units, (long long)c.rank * upr), s_len = min(n_units, s_lo + upr) - s_lo;
+    for (long long j = blockIdx.x + (long long)gridDim.x * warp; j < s_len; j += (long long)gridDim.x * wpb) {
+      const long long u = s_lo + j;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p) {
+        if (p < world) {
+          float f[4];
+          wire_load<WIRE>(static_cast<const char*>(c.data.p[p]), n_units, u, lane, f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] += f[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] *= post;
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < world) wire_store<WIRE>(static_cast<char*>(c.data.p[p]), n_units, u, lane, acc, true);
+    }
+  }
+  coll_barrier(c, ep.base + 2);
+  // phase 2: dequantise the reduced wire buffer back into my storage
+  for (int s = 0; s < world; ++s) {
+    const long long s_lo = min(n_units, (long long)s * upr), s_len = min(n_units, s_lo + upr) - s_lo;
+    for (long long j = blockIdx.x + (long long)gridDim.x * warp; j < s_len; j += (long long)gridDim.x * wpb) {
+      const long long u = s_lo + j, e = u * kUnit + lane * 4;
+      float f[4];
+      wire_load<WIRE>(my_wire, n_units, u, lane, f);
+      if (e < n) store4<S>(storage + e, f);
+    }
+  }
+  ep.commit(c, 2);
+}
+
+// =====================================================================================================
+// generic byte copy helper (width chosen from the common alignment of dst, src and n)
+// =====================================================================================================
+__device__ __forceinline__ void copy_bytes(char* dst, const char* src, long long n, long long tid, long long nthreads,
+                                           bool src_remote) {
+  const unsigned long long al = (unsigned long long)(uintptr_t)dst | (unsigned long long)(uintptr_t)src;
+  if ((al & 15) == 0) {
+    const long long nv = n >> 4;
+    for (long long i = tid; i < nv; i += nthreads) {
+      const uint4 v = src_remote ? ld_peer_v4(src + (i << 4)) : *reinterpret_cast<const uint4*>(src + (i << 4));
+      *reinterpret_cast<uint4*>(dst + (i << 4)) = v;
+    }
+    for (long long i = (nv << 4) + tid; i < n; i += nthreads) dst[i] = src[i];
+  } else if ((al & 3) == 0) {
+    const long long nv = n >> 2;
+    for (long long i = tid; i < nv; i += nthreads)
+      *reinterpret_cast<uint32_t*>(dst + (i << 2)) = src_remote ? ld_peer_u32(src + (i << 2)) : *reinterpret_cast<const uint32_t*>(src + (i << 2));
+    for (long long i = (nv << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
+  } else {
+    for (long long i = tid; i < n; i += nthreads) dst[i] = src[i];
+  }
+}
+
+// =====================================================================================================
+// K4/K5/K10  pull kernel: allgather, broadcast and alltoall are all "copy a byte range out of each
+// peer's symmetric staging buffer into my local output".
+// =====================================================================================================
+struct PullTable {
+  long long src_off[kMaxPeers];
+  long long nbytes[kMaxPeers];
+  long long dst_off[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(kThreads) pull_kernel(CollCtx c, char* out, PullTable t) {
+  EpochScope ep(c);
+  coll_barrier(c, ep.base + 1);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (int k = 0; k < c.world; ++k) {
+    const int p = (c.rank + k) % c.world;  // start with my own chunk, then walk the ring
+    if (t.nbytes[p] > 0)
+      copy_bytes(out + t.dst_off[p], static_cast<const char*>(c.data.p[p]) + t.src_off[p], t.nbytes[p], tid, nth, p != c.rank);
+  }
+  coll_barrier(c, ep.base + 2);
+  ep.commit(c, 2);
+}
+
+// K5  broadcast through the switch: the root writes its payload once with multimem.st, NVSwitch
+// replicates it into every rank's staging buffer, then each rank copies staging -> output locally.
+__global__ void __launch_bounds__(kThreads)
+bcast_multimem_kernel(CollCtx c, const char* src, char* out, long long nbytes, int root) {
+  EpochScope ep(c);
+  coll_barrier(c, ep.base + 1);
+  const long long nvec = nbytes >> 4;  // caller guarantees 16-byte multiples and alignment
+  const long long per = ceil_div_ll(nvec, gridDim.x);
+  const long long lo = min(nvec, (long long)blockIdx.x * per), hi = min(nvec, lo + per);
+  if (c.rank == root) {
+    uint4* mc = static_cast<uint4*>(c.mc);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) mc_st_v4(mc + i, *reinterpret_cast<const uint4*>(src + (i << 4)));
+  }
+  coll_barrier(c, ep.base + 2);
+  const uint4* mine = static_cast<const uint4*>(c.data.p[c.rank]);
+  if (out != nullptr && (c.rank != root || out != src))
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) *reinterpret_cast<uint4*>(out + (i << 4)) = ld_peer_v4(mine + i);
+  coll_barrier(c, ep.base + 3);  // nobody reuses staging until every rank has drained it
+  ep.commit(c, 3);
+}
+
+// =====================================================================================================
+// K10  reduce-scatter: rank r reduces elements [lo, lo+cnt) of every peer's staging buffer into its
+// local output (phase 1 of the two-shot algorithm on its own).
+// =====================================================================================================
+template <typename T> __device__ __forceinline__ T ld_scalar_peer(const T* p) { return __ldcv(p); }
+template <> __device__ __forceinline__ __nv_bfloat16 ld_scalar_peer(const __nv_bfloat16* p) {
+  unsigned short u = __ldcv(reinterpret_cast<const unsigned short*>(p));
+  return *reinterpret_cast<__nv_bfloat16*>(&u);
+}
+template <> __device__ __forceinline__ __half ld_scalar_peer(const __half* p) {
+  unsigned short u = __ldcv(reinterpret_cast<const unsigned short*>(p));
+  return *reinterpret_cast<__half*>(&u);
+}
+template <typename T> __device__ __forceinline__ typename VecTraits<T>::Acc to_acc(T v) { return (typename VecTraits<T>::Acc)v; }
+template <> __device__ __forceinline__ float to_acc(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_acc(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_acc(typename VecTraits<T>::Acc v) { return (T)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_acc(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_acc(float v) { return __float2half_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+reducescatter_kernel(CollCtx c, T* out, long long lo, long long cnt, int op, float pre, float post) {
+  using Tr = VecTraits<T>;
+  EpochScope ep(c);
+  coll_barrier(c, ep.base + 1);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const int world = c.world;
+  const bool vec_ok = ((lo * (long long)sizeof(T)) & 15) == 0 && (cnt % Tr::N) == 0 && (((uintptr_t)out) & 15) == 0;
+  if (vec_ok) {
+    const long long v0 = lo / Tr::N, nv = cnt / Tr::N;
+    for (long long i = tid; i < nv; i += nth) {
+      uint4 v[kMaxPeers];
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < world) v[p] = ld_peer_v4(static_cast<const uint4*>(c.data.p[p]) + v0 + i);
+      reinterpret_cast<uint4*>(out)[i] = reduce_vectors<T>(v, world, op, pre, post);
+    }
+  } else {
+    for (long long i = tid; i < cnt; i += nth) {
+      typename Tr::Acc acc = scale_val(to_acc<T>(ld_scalar_peer<T>(static_cast<const T*>(c.data.p[0]) + lo + i)), pre);
+      for (int p = 1; p < world; ++p)
+        acc = reduce_op(acc, scale_val(to_acc<T>(ld_scalar_peer<T>(static_cast<const T*>(c.data.p[p]) + lo + i)), pre), op);
+      out[i] = from_acc<T>(scale_val(acc, post));
+    }
+  }
+  coll_barrier(c, ep.base + 2);
+  ep.commit(c, 2);
+}
+
+// =====================================================================================================
+// K3  batched pack / unpack between user tensors and the symmetric staging buffer (pointer table in
+// device memory; blockIdx.y = table entry).  A null user pointer packs zeros (joined rank).
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+pack_kernel(char* staging, const unsigned long long* ptrs, const long long* offs, const long long* sizes, int to_staging) {
+  const int e = blockIdx.y;
+  char* user = reinterpret_cast<char*>(ptrs[e]);
+  char* st = staging + offs[e];
+  const long long n = sizes[e];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (to_staging) {
+    if (user == nullptr) {
+      for (long long i = tid; i < n; i += nth) st[i] = 0;
+    } else {
+      copy_bytes(st, user, n, tid, nth, false);
+    }
+  } else if (user != nullptr) {
+    copy_bytes(user, st, n, tid, nth, false);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_kernel(T* p, long long n, float s) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = from_acc<T>(scale_val(to_acc<T>(p[i]), s));
+}
+
+// ---- host-side dispatch ----------------------------------------------------------------------------------
+static int pick_blocks(const Comm* c, long long work_items, int per_block) {
+  long long b = ceil_div_ll(work_items, per_block);
+  if (b < 1) b = 1;
+  if (b > c->max_blocks) b = c->max_blocks;
+  return (int)b;
+}
+
+#define LAUNCH_CHECK(c)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                         \
+    if (_e != cudaSuccess) {                                                                     \
+      (c)->last_error = std::string("kernel launch failed: ") + cudaGetErrorString(_e);          \
+      return -1;                                                                                 \
+    }                                                                                            \
+    (c)->launches++;                                                                             \
+  } while (0)
+
+template <typename T>
+static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int op, float pre, float post, int algo,
+                              cudaStream_t s) {
+  const long long nvec = ceil_div_ll(numel * (long long)sizeof(T), 16);
+  const long long bytes = nvec * 16;
+  constexpr bool mc_type = std::is_same<T, float>::value || std::is_same<T, __nv_bfloat16>::value || std::is_same<T, __half>::value;
+  if (algo == 0) {
+    if (c->world == 1) algo = 1;
+    else if (bytes <= (long long)c->oneshot_max_bytes && nvec <= (long long)c->max_blocks * kThreads * kOneShotR) algo = 1;
+    else if (ctx.mc != nullptr && mc_type && op == kSum) algo = 3;
+    else algo = 2;
+  }
+  if (algo == 1) {
+    if (nvec > (long long)kMaxBlocks * kThreads * kOneShotR) algo = 2;
+  }
+  if (algo == 3 && (ctx.mc == nullptr || !mc_type || op != kSum)) {
+    c->last_error = "multimem allreduce needs a multicast-bound buffer, a float type and op=sum";
+    return -1;
+  }
+  if (algo == 1) {
+    int blocks = (int)ceil_div_ll(nvec, (long long)kThreads * kOneShotR);
+    if (blocks < 1) blocks = 1;
+    allreduce_oneshot_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, nvec, op, pre, post);
+  } else if (algo == 2) {
+    const int blocks = pick_blocks(c, ceil_div_ll(nvec, c->world), kThreads * 2);
+    allreduce_twoshot_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, nvec, op, pre, post);
+  } else {
+    if constexpr (mc_type) {
+      const int blocks = pick_blocks(c, ceil_div_ll(nvec, c->world), kThreads * 4);
+      allreduce_multimem_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, nvec, pre * post);
+    }
+  }
+  LAUNCH_CHECK(c);
+  return algo;
+}
+
+}  // namespace sdlc
+
+using namespace sdlc;
+
+extern "C" {
+
+// In-place allreduce of `numel` elements at byte `offset` of symmetric buffer `buf`.
+// algo: 0 auto, 1 one-shot, 2 two-shot P2P, 3 two-shot NVLS.  Returns the algorithm used or -1.
+int sdlc_allreduce(void* h, int channel, int buf, long long offset, long long numel, int dtype, int op,
+                   float pre, float post, int algo, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  const CollCtx ctx = c->make_ctx(channel, buf, (size_t)offset);
+  if (op == kAvg) {
+    op = kSum;
+    post /= (float)c->world;
+  }
+  switch (dtype) {
+    case kF32: return launch_allreduce_t<float>(c, ctx, numel, op, pre, post, algo, s);
+    case kBF16: return launch_allreduce_t<__nv_bfloat16>(c, ctx, numel, op, pre, post, algo, s);
+    case kF16: return launch_allreduce_t<__half>(c, ctx, numel, op, pre, post, algo, s);
+    case kF64: return launch_allreduce_t<double>(c, ctx, numel, op, pre, post, algo, s);
+    case kI32: return launch_allreduce_t<int32_t>(c, ctx, numel, op, pre, post, algo, s);
+    case kI64: return launch_allreduce_t<int64_t>(c, ctx, numel, op, pre, post, algo, s);
+    case kU8: case kBool: return launch_allreduce_t<uint8_t>(c, ctx, numel, op, pre, post, algo, s);
+    case kI8: return launch_allreduce_t<int8_t>(c, ctx, numel, op, pre, post, algo, s);
+    default: c->last_error = "unsupported dtype for CUDA allreduce"; return -1;
+  }
+}
+
+// bytes of symmetric wire buffer needed for `numel` elements in wire format `wire`
+long long sdlc_wire_bytes(long long numel, int wire) {
+  const long long units = ceil_div_ll(numel, kUnit);
+  return wire == kWireFP8 ? units * kUnit + units * 4 : units * kUnit * 2;
+}
+
+// Allreduce of a local storage tensor through a (smaller) symmetric wire buffer.
+int sdlc_allreduce_wire(void* h, int channel, void* storage, long long numel, int dtype, int wire, int wire_buf,
+                        long long wire_off, float pre, float post, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  const CollCtx ctx = c->make_ctx(channel, wire_buf, (size_t)wire_off);
+  const long long units = ceil_div_ll(numel, kUnit);
+  const int blocks = pick_blocks(c, ceil_div_ll(units, c->world), kThreads / 32 * 4);
+  if (dtype == kF32) {
+    float* p = static_cast<float*>(storage);
+    if (wire == kWireBF16) allreduce_wire_kernel<float, kWireBF16><<<blocks, kThreads, 0, s>>>(ctx, p, numel, pre, post);
+    else if (wire == kWireF16) allreduce_wire_kernel<float, kWireF16><<<blocks, kThreads, 0, s>>>(ctx, p, numel, pre, post);
+    else if (wire == kWireFP8) allreduce_wire_kernel<float, kWireFP8><<<blocks, kThreads, 0, s>>>(ctx, p, numel, pre, post);
+    else { c->last_error = "bad wire format"; return -1; }
+  } else if (dtype == kBF16) {
+    __nv_bfloat16* p = static_cast<__nv_bfloat16*>(storage);
+    if (wire == kWireFP8) allreduce_wire_kernel<__nv_bfloat16, kWireFP8><<<blocks, kThreads, 0, s>>>(ctx, p, numel, pre, post);
+    else { c->last_error = "bf16 storage supports the fp8 wire format only"; return -1; }
+  } else {
+    c->last_error = "wire-format allreduce supports fp32 and bf16 storage";
+    return -1;
+  }
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int sdlc_barrier(void* h, int channel, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  const CollCtx ctx = c->make_ctx(channel, c->pad_buf, 0);
+  barrier_kernel<<<1, kThreads, 0, s>>>(ctx);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+// allgather / broadcast / alltoall: pull byte ranges out of the peers' staging buffers
+int sdlc_pull(void* h, int channel, int buf, void* out, const long long* src_off, const long long* nbytes,
+              const long long* dst_off, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  const CollCtx ctx = c->make_ctx(channel, buf, 0);
+  PullTable t;
+  long long total = 0;
+  for (int p = 0; p < kMaxPeers; ++p) {
+    t.src_off[p] = p < c->world ? src_off[p] : 0;
+    t.nbytes[p] = p < c->world ? nbytes[p] : 0;
+    t.dst_off[p] = p < c->world ? dst_off[p] : 0;
+    total += t.nbytes[p];
+  }
+  const int blocks = pick_blocks(c, ceil_div_ll(total, 16), kThreads * 4);
+  pull_kernel<<<blocks, kThreads, 0, s>>>(ctx, static_cast<char*>(out), t);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int sdlc_bcast_multimem(void* h, int channel, int buf, const void* src, void* out, long long nbytes, int root,
+                        unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  const CollCtx ctx = c->make_ctx(channel, buf, 0);
+  if (ctx.mc == nullptr || (nbytes & 15) != 0) {
+    c->last_error = "multimem broadcast needs a multicast-bound staging buffer and 16-byte multiples";
+    return -1;
+  }
+  const int blocks = pick_blocks(c, nbytes >> 4, kThreads * 4);
+  bcast_multimem_kernel<<<blocks, kThreads, 0, s>>>(ctx, static_cast<const char*>(src), static_cast<char*>(out), nbytes, root);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int sdlc_reducescatter(void* h, int channel, int buf, void* out, long long lo, long long cnt, int dtype, int op,
+                       float pre, float post, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  const CollCtx ctx = c->make_ctx(channel, buf, 0);
+  if (op == kAvg) {
+    op = kSum;
+    post /= (float)c->world;
+  }
+  const int blocks = pick_blocks(c, cnt, kThreads * 4);
+#define RS(T) reducescatter_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, static_cast<T*>(out), lo, cnt, op, pre, post)
+  switch (dtype) {
+    case kF32: RS(float); break;
+    case kBF16: RS(__nv_bfloat16); break;
+    case kF16: RS(__half); break;
+    case kF64: RS(double); break;
+    case kI32: RS(int32_t); break;
+    case kI64: RS(int64_t); break;
+    default: c->last_error = "unsupported dtype for CUDA reducescatter"; return -1;
+  }
+#undef RS
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+// Batched copy between n user tensors and the staging buffer of `buf` (to_staging=1: pack).
+int sdlc_pack(void* h, int buf, const unsigned long long* ptrs, const long long* offs, const long long* sizes, int n,
+              int to_staging, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  if (n <= 0) return 0;
+  if (n > 1024) {
+    c->last_error = "too many tensors in one pack";
+    return -1;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int slot = c->table_next;
+  c->table_next = (c->table_next + 1) % 16;
+  cudaEventSynchronize(c->table_events[slot]);  // slot reuse: previous user has consumed the table
+  char* hb = static_cast<char*>(c->table_host) + (size_t)slot * 3 * 1024 * 8;
+  char* db = static_cast<char*>(c->table_dev) + (size_t)slot * 3 * 1024 * 8;
+  memcpy(hb, ptrs, (size_t)n * 8);
+  memcpy(hb + 1024 * 8, offs, (size_t)n * 8);
+  memcpy(hb + 2 * 1024 * 8, sizes, (size_t)n * 8);
+  cudaMemcpyAsync(db, hb, 3 * 1024 * 8, cudaMemcpyHostToDevice, s);
+  long long maxb = 0;
+  for (int i = 0; i < n; ++i) maxb = sizes[i] > maxb ? sizes[i] : maxb;
+  int bx = (int)ceil_div_ll(maxb, 256 * 16 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, n);
+  pack_kernel<<<grid, 256, 0, s>>>(static_cast<char*>(c->bufs[buf].ptrs[c->rank]),
+                                   reinterpret_cast<const unsigned long long*>(db),
+                                   reinterpret_cast<const long long*>(db + 1024 * 8),
+                                   reinterpret_cast<const long long*>(db + 2 * 1024 * 8), to_staging);
+  cudaEventRecord(c->table_events[slot], s);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int sdlc_scale(void* h, void* p, long long n, int dtype, float s, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int blocks = (int)ceil_div_ll(n, 256 * 8);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 1184) blocks = 1184;
+  switch (dtype) {
+    case kF32: scale_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float*>(p), n, s); break;
+    case kBF16: scale_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(p), n, s); break;
+    case kF16: scale_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<__half*>(p), n, s); break;
+    case kF64: scale_kernel<double><<<blocks, 256, 0, st>>>(static_cast<double*>(p), n, s); break;
+    default: return 0;
+  }
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// Fused "reduce-scatter + optimizer + all-gather" step (BASELINE.json north
+// star: "FUSES the reduction with the gradient cast/scale ... so no separate NCCL call or
+// elementwise kernel runs on that path").
+//
+// Gradients AND parameters of a bucket live in symmetric buffers.  Rank r owns slice r:
+//   g      = (sum over peers of grad[slice r]) * scale        (P2P loads or multimem.ld_reduce)
+//   p_new  = optimizer(p_old, g, state[slice r])               (SGD-momentum / Adam / AdamW, fp32 math,
+//                                                               optional fp32 master weights)
+//   param[slice r] on EVERY rank = p_new                       (P2P stores or multimem.st)
+// One launch replaces allreduce + foreach-optimizer kernels, and the optimizer state (and master
+// weights) are sharded 1/N per GPU.
+#include <cstring>
+
+#include "comm.h"
+
+namespace sdlc {
+
+struct OptimArgs {
+  int kind;        // 0 SGD, 1 Adam (L2 in grad), 2 AdamW (decoupled)
+  float lr, weight_decay;
+  float momentum, dampening;
+  int nesterov, first_step;
+  float beta1, beta2, eps, bias_c1, bias_c2;  // bias_c = 1 - beta^t
+};
+
+template <typename T> __device__ __forceinline__ uint4 mc_ld_reduce_t(const void* p);
+template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<float>(const void* p) { return mc_ld_reduce_f32(p); }
+template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<__nv_bfloat16>(const void* p) { return mc_ld_reduce_bf16(p); }
+template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<__half>(const void* p) { return mc_ld_reduce_f16(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+fused_step_kernel(CollCtx g, PeerPtrs params, void* params_mc, float* __restrict__ s1, float* __restrict__ s2,
+                  float* __restrict__ master, long long nvec, float scale, OptimArgs a) {
+  using Tr = VecTraits<T>;
+  EpochScope ep(g);
+  coll_barrier(g, ep.base + 1);
+  const int world = g.world;
+  const long long per = (nvec + world - 1) / world;
+  const long long lo = min(nvec, (long long)g.rank * per), hi = min(nvec, lo + per);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool mc_in = g.mc != nullptr, mc_out = params_mc != nullptr;
+  for (long long idx = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < hi; idx += stride) {
+    float gr[Tr::N];
+    if (mc_in) {
+      const uint4 v = mc_ld_reduce_t<T>(static_cast<const uint4*>(g.mc) + idx);
+      vec_unpack<T>(v, gr);
+    } else {
+      uint4 v[kMaxPeers];
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < world) v[p] = ld_peer_v4(static_cast<const uint4*>(g.data.p[p]) + idx);
+      float t[Tr::N];
+      vec_unpack<T>(v[0], gr);
+#pragma unroll
+      for (int p = 1; p < kMaxPeers; ++p)
+        if (p < world) {
+          vec_unpack<T>(v[p], t);
+#pragma unroll
+          for (int i = 0; i < Tr::N; ++i) gr[i] += t[i];
+        }
+    }
+    const long long k0 = (idx - lo) * Tr::N;
+    float pw[Tr::N];
+    if (master != nullptr) {
+#pragma unroll
+      for (int i = 0; i < Tr::N; ++i) pw[i] = master[k0 + i];
+    } else {
+      vec_unpack<T>(static_cast<const uint4*>(params.p[g.rank])[idx], pw);
+    }
+#pragma unroll
+    for (int i = 0; i < Tr::N; ++i) {
+      float gi = gr[i] * scale, p = pw[i];
+      if (a.kind == 0) {
+        gi = fmaf(a.weight_decay, p, gi);
+        if (a.momentum != 0.f) {
+          float b = a.first_step ? gi : fmaf(a.momentum, s1[k0 + i], (1.f - a.dampening) * gi);
+          s1[k0 + i] = b;
+          gi = a.nesterov ? fmaf(a.momentum, b, gi) : b;
+        }
+        p = fmaf(-a.lr, gi, p);
+      } else {
+        if (a.kind == 1) gi = fmaf(a.weight_decay, p, gi);
+        else p *= (1.f - a.lr * a.weight_decay);
+        const float m = fmaf(a.beta1, s1[k0 + i], (1.f - a.beta1) * gi);
+        const float v = fmaf(a.beta2, s2[k0 + i], (1.f - a.beta2) * gi * gi);
+        s1[k0 + i] = m;
+        s2[k0 + i] = v;
+        const float denom = sqrtf(v) / sqrtf(a.bias_c2) + a.eps;
+        p = fmaf(-(a.lr / a.bias_c1), m / denom, p);
+      }
+      pw[i] = p;
+    }
+    if (master != nullptr) {
+#pragma unroll
+      for (int i = 0; i < Tr::N; ++i) master[k0 + i] = pw[i];
+    }
+    const uint4 out = vec_pack<T>(pw);
+    if (mc_out) {
+      mc_st_v4(static_cast<uint4*>(params_mc) + idx, out);
+    } else {
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < world) st_peer_v4(static_cast<uint4*>(params.p[p]) + idx, out);
+    }
+  }
+  coll_barrier(g, ep.base + 2);
+  ep.commit(g, 2);
+}
+
+}  // namespace sdlc
+
+using namespace sdlc;
+
+extern "C" {
+
+// args: float[16] = {kind, lr, wd, momentum, dampening, nesterov, first_step, beta1, beta2, eps, bias_c1, bias_c2}
+int sdlc_fused_step(void* h, int channel, int grad_buf, int param_buf, long long numel, int dtype, float* s1, float* s2,
+                    float* master, float scale, const float* args, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  CollCtx g = c->make_ctx(channel, grad_buf, 0);
+  const SymmBuffer& pb = c->bufs[param_buf];
+  PeerPtrs pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int r = 0; r < c->world; ++r) pp.p[r] = pb.ptrs[r];
+  void* pmc = (pb.mc && c->use_mc) ? pb.mc : nullptr;
+  OptimArgs a;
+  a.kind = (int)args[0]; a.lr = args[1]; a.weight_decay = args[2]; a.momentum = args[3]; a.dampening = args[4];
+  a.nesterov = (int)args[5]; a.first_step = (int)args[6]; a.beta1 = args[7]; a.beta2 = args[8]; a.eps = args[9];
+  a.bias_c1 = args[10]; a.bias_c2 = args[11];
+  const size_t esz = dtype == kF32 ? 4 : 2;
+  const long long nvec = (numel * (long long)esz + 15) / 16;
+  long long blocks = ((nvec + c->world - 1) / c->world + kThreads - 1) / kThreads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > c->max_blocks) blocks = c->max_blocks;
+  if (dtype == kF32) {
+    fused_step_kernel<float><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, a);
+  } else if (dtype == kBF16) {
+    fused_step_kernel<__nv_bfloat16><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, a);
+  } else if (dtype == kF16) {
+    fused_step_kernel<__half><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, a);
+  } else {
+    c->last_error = "fused optimizer step supports fp32 / bf16 / fp16 parameters";
+    return -1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    c->last_error = std::string("fused_step launch failed: ") + cudaGetErrorString(e);
+    return -1;
+  }
+  c->launches++;
+  return 0;
+}
+
+// elements of optimizer state this rank must allocate for a bucket of `numel` elements
+long long sdlc_fused_state_elems(void* h, long long numel, int dtype) {
+  Comm* c = static_cast<Comm*>(h);
+  const size_t esz = dtype == kF32 ? 4 : 2;
+  const long long n_per_vec = 16 / (long long)esz;
+  const long long nvec = (numel * (long long)esz + 15) / 16;
+  const long long per = (nvec + c->world - 1) / c->world;
+  return per * n_per_vec;
+}
+
+// first element (in units of elements) of this rank's slice - for checkpointing the sharded state
+long long sdlc_fused_slice_start(void* h, long long numel, int dtype) {
+  Comm* c = static_cast<Comm*>(h);
+  const size_t esz = dtype == kF32 ? 4 : 2;
+  const long long n_per_vec = 16 / (long long)esz;
+  const long long nvec = (numel * (long long)esz + 15) / 16;
+  const long long per = (nvec + c->world - 1) / c->world;
+  long long lo = (long long)c->rank * per;
+  if (lo > nvec) lo = nvec;
+  return lo * n_per_vec;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""ResNet-50 (v1.5: stride on the 3x3 conv) for the flagship data-parallel benchmark
+(BASELINE.json config 2: "ResNet-50 torch DistributedOptimizer via HorovodRunner(np=-8)").
+
+Layout is NHWC (``channels_last``) bf16 end to end.  Convolutions are plain library calls
+(cuDNN); everything between two convolutions - batch-norm statistics, normalise, residual add,
+ReLU - runs in the fused sm_100a kernels of :mod:`spark_deep_learning_b200.ops.norm` when
+``fused=True`` (one read + one write of the activation instead of five).
+"""
+import torch
+from torch import nn
+
+
+class _ConvBN(nn.Module):
+    """conv -> batch-norm (-> +residual) (-> ReLU) with an optional fused epilogue."""
+
+    def __init__(self, cin, cout, k, stride=1, relu=True, fused=False, zero_init=False):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+        if zero_init:
+            nn.init.zeros_(self.bn.weight)
+        self.relu = relu
+        self.fused = fused
+        nn.init.kaiming_normal_(self.conv.weight, mode="fan_out", nonlinearity="relu")
+
+    def forward(self, x, residual=None):
+        y = self.conv(x)
+        if self.fused and y.is_cuda and self.training:
+            from spark_deep_learning_b200.ops import norm
+            return norm.batch_norm_act(y, self.bn, residual, self.relu)
+        y = self.bn(y)
+        if residual is not None:
+            y = y + residual
+        return torch.relu_(y) if self.relu else y
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, cin, width, stride, fused):
+        super().__init__()
+        cout = width * self.expansion
+        self.a = _ConvBN(cin, width, 1, fused=fused)
+        self.b = _ConvBN(width, width, 3, stride=stride, fused=fused)
+        self.c = _ConvBN(width, cout, 1, relu=True, fused=fused, zero_init=True)
+        self.down = None
+        if stride != 1 or cin != cout:
+            self.down = _ConvBN(cin, cout, 1, stride=stride, relu=False, fused=fused)
+
+    def forward(self, x):
+        idt = x if self.down is None else self.down(x)
+        return self.c(self.b(self.a(x)), residual=idt)
+
+
+class ResNet(nn.Module):
+    def __init__(self, layers=(3, 4, 6, 3), num_classes=1000, fused=False):
+        super().__init__()
+        self.stem = _ConvBN(3, 64, 7, stride=2, fused=fused)
+        self.pool = nn.MaxPool2d(3, stride=2, padding=1)
+        blocks, cin = [], 64
+        for i, n in enumerate(layers):
+            width = 64 * 2 ** i
+            for j in range(n):
+                blocks.append(Bottleneck(cin, width, (2 if i > 0 else 1) if j == 0 else 1, fused))
+                cin = width * Bottleneck.expansion
+        self.blocks = nn.Sequential(*blocks)
+        self.fc = nn.Linear(cin, num_classes)
+
+    def forward(self, x):
+        x = self.pool(self.stem(x))
+        x = self.blocks(x)
+        x = torch.flatten(torch.nn.functional.adaptive_avg_pool2d(x, 1), 1)
+        return self.fc(x)
+
+
+def resnet50(num_classes=1000, fused=False):
+    return ResNet((3, 4, 6, 3), num_classes, fused)
+
+
+def resnet18ish(num_classes=10, fused=False):
+    """Tiny bottleneck net for smoke tests."""
+    return ResNet((1, 1, 1, 1), num_classes, fused)

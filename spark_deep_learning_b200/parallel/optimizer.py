@@ -99,16 +99,20 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         hvd = self._hvd
         comm = hvd.comm_backend()
         trainable = [p for p in params if p.requires_grad]
+        group_index = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
+        self._bucket_group = {}
         cur = {}
         for p in reversed(trainable):
             if p.is_sparse:
                 raise ValueError("sparse parameters are not supported by DistributedOptimizer")
-            key = (p.dtype, p.device)
+            # one param group per bucket: the fused kernel takes per-launch hyper-parameters
+            key = (p.dtype, p.device, group_index[id(p)])
             b = cur.get(key)
             esz = p.element_size()
             if b is None or (b.numel * esz >= self._bucket_bytes):
                 b = _Bucket(len(self._buckets), p.dtype, p.device)
                 self._buckets.append(b)
+                self._bucket_group[b.index] = group_index[id(p)]
                 cur[key] = b
             b.params.append(p)
             b.offsets.append(b.numel)
@@ -139,6 +143,9 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             b.pending = len(b.params)
         if comm is not None and any(b.sym is not None for b in self._buckets):
             comm.sync_all()  # all ranks finished zeroing / copying before the first kernel
+
+    def _group_of_bucket(self, b):
+        return self.param_groups[self._bucket_group[b.index]]
 
     def _register_hooks(self):
         for b in self._buckets:

@@ -292,7 +292,7 @@ class FdServer(object):
                     deadline = time.time() + 120.0
                     while key not in self._fds and time.time() < deadline and not self._closed:
                         self._cv.wait(0.5)
-                    fd = self._fds.get(key)
+                    fd = self._fds.get(key)  # None = the owner failed to export it
                 if fd is None:
                     socket.send_fds(conn, [b"N"], [])
                 else:
