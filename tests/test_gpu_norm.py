@@ -1,0 +1,74 @@
+"""Numerics of the fused BN(+add)(+ReLU) kernels vs a plain PyTorch fp32 reference."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, b, res, relu, eps):
+    xf = x.float()
+    y = torch.nn.functional.batch_norm(xf, None, None, w, b, True, 0.1, eps)
+    if res is not None:
+        y = y + res.float()
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("c,hw,n", [(64, 56, 8), (256, 14, 16), (2048, 7, 4), (512, 28, 3), (1024, 5, 2)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("with_res,relu", [(False, True), (True, True), (False, False)])
+def test_bn_act_forward_backward(c, hw, n, dtype, with_res, relu):
+    from spark_deep_learning_b200.ops import norm
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = (torch.randn(n, c, hw, hw, device=dev) * 2 + 0.5).to(dtype).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(n, c, hw, hw, device=dev).to(dtype).contiguous(memory_format=torch.channels_last) if with_res else None
+    bn = torch.nn.BatchNorm2d(c).to(dev)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    assert norm.supported(x)
+    x1 = x.clone().requires_grad_(True)
+    r1 = res.clone().requires_grad_(True) if with_res else None
+    y = norm.batch_norm_act(x1, bn, r1, relu)
+    g = torch.randn_like(y)
+    y.backward(g)
+    # reference in fp32 on the same (rounded) inputs
+    x2 = x.float().clone().requires_grad_(True)
+    r2 = res.float().clone().requires_grad_(True) if with_res else None
+    w2 = bn.weight.detach().clone().requires_grad_(True)
+    b2 = bn.bias.detach().clone().requires_grad_(True)
+    yr = _ref(x2, w2, b2, r2, relu, bn.eps)
+    yr.backward(g.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 2e-4
+    assert torch.allclose(y.float(), yr, rtol=tol, atol=tol), (y.float() - yr).abs().max()
+    scale = x2.grad.abs().max().item() + 1e-6
+    assert (x1.grad.float() - x2.grad).abs().max().item() / scale < (3e-2 if dtype == torch.bfloat16 else 1e-3)
+    assert torch.allclose(bn.weight.grad, w2.grad, rtol=3e-2 if dtype == torch.bfloat16 else 1e-3,
+                          atol=(3e-2 if dtype == torch.bfloat16 else 1e-3) * w2.grad.abs().max().item())
+    assert torch.allclose(bn.bias.grad, b2.grad, rtol=3e-2 if dtype == torch.bfloat16 else 1e-3,
+                          atol=(3e-2 if dtype == torch.bfloat16 else 1e-3) * b2.grad.abs().max().item())
+    if with_res:
+        assert (r1.grad.float() - r2.grad).abs().max().item() < (2e-2 if dtype == torch.bfloat16 else 1e-5)
+    # running statistics follow torch semantics
+    m = x.float().mean((0, 2, 3))
+    assert torch.allclose(bn.running_mean, 0.1 * m, rtol=1e-3, atol=1e-3)
+
+
+def test_resnet_fused_matches_unfused():
+    from spark_deep_learning_b200 import models
+    torch.manual_seed(0)
+    a = models.resnet18ish(num_classes=10, fused=True).cuda().to(memory_format=torch.channels_last)
+    b = models.resnet18ish(num_classes=10, fused=False).cuda().to(memory_format=torch.channels_last)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(16, 3, 64, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), device="cuda")
+    outs = []
+    for m in (a, b):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(m(x), y)
+        loss.backward()
+        outs.append((loss.item(), m.fc.weight.grad.clone(), m.stem.conv.weight.grad.clone()))
+    assert abs(outs[0][0] - outs[1][0]) < 5e-2
+    for k in (1, 2):
+        d = (outs[0][k] - outs[1][k]).abs().max().item() / (outs[1][k].abs().max().item() + 1e-6)
+        assert d < 0.15, (k, d)
