@@ -18,6 +18,7 @@ sys.path.insert(0, ROOT)
 
 
 def sweep(max_mb=1024, iters=20, warmup=5, dtypes=("float32", "bfloat16"), with_nccl=True, wires=("bf16", "fp8")):
+    import os
     import torch
     import sparkdl.hvd as hvd
     from spark_deep_learning_b200.parallel import core
@@ -89,6 +90,16 @@ def sweep(max_mb=1024, iters=20, warmup=5, dtypes=("float32", "bfloat16"), with_
                 ms = timed(fn, nb)
                 row[name + "_us"] = round(ms * 1e3, 2)
                 row[name + "_busbw"] = round(2 * (world - 1) / world * nb / (ms * 1e-3) / 1e9, 2) if world > 1 else None
+            if nb >= (64 << 20):   # how many CTAs does it take to saturate NVLink?
+                for ctas in (64, 128):
+                    lib.sdlc_comm_set_max_blocks(comm._h, ctas)
+                    for name, algo in algos[1:]:
+                        def fnb(algo=algo, n=n):
+                            rc = lib.sdlc_allreduce(comm._h, 2, buf.id, 0, n, code, 0, 1.0, 1.0 / world, algo, stream)
+                            assert rc >= 0, comm._err()
+                        ms = timed(fnb, nb)
+                        row["%s_ctas%d_busbw" % (name, ctas)] = round(2 * (world - 1) / world * nb / (ms * 1e-3) / 1e9, 2) if world > 1 else None
+                lib.sdlc_comm_set_max_blocks(comm._h, int(os.environ.get("SPARKDL_COMM_CTAS", "32")))
             if dname == "float32" and nb >= (1 << 16):
                 for w in wires:
                     def fnw(w=w, n=n):

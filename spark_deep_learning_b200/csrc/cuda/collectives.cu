@@ -146,13 +146,14 @@ allreduce_multimem_kernel(CollCtx c, long long nvec, float scale) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   uint4* mc = static_cast<uint4*>(c.mc);
   const bool do_scale = scale != 1.0f;
-  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += 4 * stride) {
-    uint4 v[4];
+  constexpr int U = 8;  // independent ld_reduce in flight per thread (NVLink latency ~2 us)
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += U * stride) {
+    uint4 v[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
       if (i0 + u * stride < hi) v[u] = mc_ld_reduce<T>(mc + i0 + u * stride);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
       if (i0 + u * stride < hi) mc_st_v4(mc + i0 + u * stride, do_scale ? scale_vector<T>(v[u], scale) : v[u]);
   }
   coll_barrier(c, ep.base + 2);
@@ -491,7 +492,7 @@ static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int 
     allreduce_twoshot_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, nvec, op, pre, post);
   } else {
     if constexpr (mc_type) {
-      const int blocks = pick_blocks(c, ceil_div_ll(nvec, c->world), kThreads * 4);
+      const int blocks = pick_blocks(c, ceil_div_ll(nvec, c->world), kThreads * 8);
       allreduce_multimem_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, nvec, pre * post);
     }
   }

@@ -1,0 +1,143 @@
+"""sparkdl.xgboost: the reference's doctests (xgboost.py:223-239, 311-326) as executable tests, the
+param surface of SURVEY.md §2b, persistence, and data-parallel training on CPU workers."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from sparkdl.xgboost import (Vectors, XgboostClassifier, XgboostClassifierModel, XgboostRegressor,
+                             XgboostRegressorModel)
+
+
+def _toy(n=3000, f=8, seed=0, nan_frac=0.1):
+    rng = np.random.RandomState(seed)
+    X = rng.randn(n, f).astype(np.float32)
+    y = (2 * X[:, 0] + np.sin(3 * X[:, 1]) + 1.5 * (X[:, 2] > 0.3) + 0.1 * rng.randn(n)).astype(np.float32)
+    X[rng.rand(n, f) < nan_frac] = np.nan
+    return X, y
+
+
+def test_reference_doctest_regressor():
+    df_train = pd.DataFrame({
+        "features": [Vectors.dense(1.0, 2.0, 3.0), Vectors.sparse(3, {1: 1.0, 2: 5.5}),
+                     Vectors.dense(4.0, 5.0, 6.0), Vectors.sparse(3, {1: 6.0, 2: 7.5})],
+        "label": [0, 1, 2, 3], "isVal": [False, False, True, True], "weight": [1.0, 2.0, 1.0, 2.0]})
+    df_test = pd.DataFrame({"features": [Vectors.dense(1.0, 2.0, 3.0), Vectors.sparse(3, {1: 1.0, 2: 5.5})]})
+    reg = XgboostRegressor(max_depth=5, missing=0.0, validationIndicatorCol='isVal', weightCol='weight',
+                           early_stopping_rounds=1, eval_metric='rmse')
+    model = reg.fit(df_train)
+    assert isinstance(model, XgboostRegressorModel)
+    out = model.transform(df_test)
+    assert list(out.columns) == ["features", "prediction"] and len(out) == 2
+
+
+def test_reference_doctest_classifier():
+    df_train = pd.DataFrame({
+        "features": [Vectors.dense(1.0, 2.0, 3.0), Vectors.sparse(3, {1: 1.0, 2: 5.5}),
+                     Vectors.dense(4.0, 5.0, 6.0), Vectors.sparse(3, {1: 6.0, 2: 7.5})],
+        "label": [0, 1, 0, 1], "isVal": [False, False, True, True], "weight": [1.0, 2.0, 1.0, 2.0]})
+    clf = XgboostClassifier(max_depth=5, missing=0.0, validationIndicatorCol='isVal', weightCol='weight',
+                            early_stopping_rounds=1, eval_metric='logloss')
+    model = clf.fit(df_train)
+    assert isinstance(model, XgboostClassifierModel)
+    out = model.transform(pd.DataFrame({"features": [Vectors.dense(1.0, 2.0, 3.0)]}))
+    assert {"rawPrediction", "prediction", "probability"} <= set(out.columns)
+    assert abs(sum(out["probability"][0]) - 1.0) < 1e-6 and len(out["rawPrediction"][0]) == 2
+
+
+def test_param_surface():
+    reg = XgboostRegressor()
+    for name in ("missing", "callbacks", "num_workers", "use_gpu", "force_repartition", "use_external_storage",
+                 "external_storage_precision", "baseMarginCol", "featuresCol", "labelCol", "weightCol",
+                 "predictionCol", "validationIndicatorCol", "max_depth", "n_estimators", "learning_rate"):
+        assert reg.hasParam(name), name
+    clf = XgboostClassifier()
+    assert clf.hasParam("probabilityCol") and clf.hasParam("rawPredictionCol")
+    assert np.isnan(reg.getOrDefault("missing")) and reg.getOrDefault("use_external_storage") is False
+    with pytest.raises(TypeError):
+        XgboostRegressor(num_workers="two")           # toInt converter (ref xgboost.py:63)
+    for bad in ("gpu_id", "base_margin", "validate_features", "output_margin", "eval_set", "sample_weight",
+                "sample_weight_eval_set"):
+        with pytest.raises(ValueError, match="Unsupported param"):
+            XgboostRegressor(**{bad: 1})
+    with pytest.raises(ValueError, match="Invalid param name"):
+        XgboostRegressor(no_such_param=1)
+    c = reg.copy({reg.max_depth: 3})
+    assert c.getOrDefault("max_depth") == 3 and reg.getOrDefault("max_depth") == 6
+    assert "max_depth" in reg.explainParams()
+
+
+def test_regression_quality_missing_weights_early_stopping():
+    X, y = _toy()
+    rng = np.random.RandomState(1)
+    df = pd.DataFrame({"features": list(X), "label": y, "isVal": rng.rand(len(y)) < 0.2,
+                       "w": rng.uniform(0.5, 2.0, len(y))})
+    m = XgboostRegressor(n_estimators=80, max_depth=5, learning_rate=0.2, validationIndicatorCol="isVal",
+                         weightCol="w", early_stopping_rounds=5, subsample=0.9, colsample_bytree=0.9).fit(df)
+    hist = m.evals_result()["validation_0"]["rmse"]
+    assert hist[-1] < 0.45 * hist[0]
+    b = m.get_booster()
+    assert b.best_iteration is not None and b.num_boosted_rounds <= 80
+    pred = m.transform(df)["prediction"].to_numpy()
+    assert np.sqrt(np.mean((pred - y) ** 2)) < 0.5 * y.std()
+    assert len(b.get_dump()) == len(b.trees) and b.get_score()
+
+
+def test_binary_and_multiclass():
+    X, y = _toy(2000)
+    yb = (y > np.median(y)).astype(np.float32)
+    out = XgboostClassifier(n_estimators=25, max_depth=4).fit(pd.DataFrame({"features": list(X), "label": yb})) \
+        .transform(pd.DataFrame({"features": list(X)}))
+    assert (out["prediction"].to_numpy() == yb).mean() > 0.95
+    raw = np.stack(out["rawPrediction"].to_list())
+    assert np.allclose(raw[:, 0], -raw[:, 1])
+    y3 = np.digitize(y, np.quantile(y, [0.33, 0.66])).astype(np.float32)
+    m3 = XgboostClassifier(n_estimators=20, max_depth=4).fit(pd.DataFrame({"features": list(X), "label": y3}))
+    o3 = m3.transform(pd.DataFrame({"features": list(X)}))
+    assert (o3["prediction"].to_numpy() == y3).mean() > 0.85 and len(o3["probability"][0]) == 3
+
+
+def test_persistence_warm_start_callbacks_base_margin(tmp_path):
+    X, y = _toy(1500)
+    df = pd.DataFrame({"features": list(X), "label": y, "bm": np.full(len(y), 0.25, dtype=np.float32)})
+    seen = []
+    est = XgboostRegressor(n_estimators=10, max_depth=3, callbacks=[lambda env: seen.append(env["iteration"]) or False],
+                           baseMarginCol="bm")
+    model = est.fit(df)
+    assert seen == list(range(10))
+    p = model.transform(df)["prediction"].to_numpy()
+    model.write().overwrite().save(str(tmp_path / "model"))
+    again = XgboostRegressorModel.load(str(tmp_path / "model"))
+    assert np.allclose(again.transform(df)["prediction"].to_numpy(), p)
+    est.write().overwrite().save(str(tmp_path / "est"))
+    est2 = XgboostRegressor.load(str(tmp_path / "est"))
+    assert est2.getOrDefault("max_depth") == 3 and callable(est2.getOrDefault("callbacks")[0])
+    with pytest.raises(IOError):
+        model.write().save(str(tmp_path / "model"))
+    # warm start from get_booster() (ref xgboost.py:198-199)
+    more = XgboostRegressor(n_estimators=5, max_depth=3, xgb_model=model.get_booster()).fit(df[["features", "label"]])
+    assert more.get_booster().num_boosted_rounds == 15
+
+
+def test_external_storage_rounding():
+    X, y = _toy(800, nan_frac=0.0)
+    df = pd.DataFrame({"features": list(X), "label": y})
+    m = XgboostRegressor(n_estimators=10, use_external_storage=True, external_storage_precision=3).fit(df)
+    assert np.isfinite(m.transform(df)["prediction"].to_numpy()).all()
+    with pytest.raises(ValueError):
+        XgboostRegressor(use_external_storage=True, weightCol="label").fit(df)
+
+
+def test_distributed_cpu_workers_match_single_worker(monkeypatch):
+    """num_workers=2: rows sharded over two HorovodRunner workers, histograms allreduced as exact
+    int64 sums -> the same model as single-worker training."""
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "0")
+    X, y = _toy(1200, f=6)
+    df = pd.DataFrame({"features": list(X), "label": y})
+    kw = dict(n_estimators=8, max_depth=4, learning_rate=0.3)
+    single = XgboostRegressor(**kw).fit(df).transform(df)["prediction"].to_numpy()
+    dist_model = XgboostRegressor(num_workers=2, force_repartition=True, **kw).fit(df)
+    dist = dist_model.transform(df)["prediction"].to_numpy()
+    assert dist_model.get_booster().attributes["workers"] == 2
+    assert np.allclose(single, dist, atol=1e-4), np.abs(single - dist).max()
+    with pytest.raises(ValueError, match="distributed"):
+        XgboostRegressor(num_workers=2, baseMarginCol="label").fit(df)
