@@ -349,21 +349,51 @@ __global__ void __launch_bounds__(kThreads) pull_kernel(CollCtx c, char* out, Pu
 
 // K5  broadcast through the switch: the root writes its payload once with multimem.st, NVSwitch
 // replicates it into every rank's staging buffer, then each rank copies staging -> output locally.
+// 16-byte read / write of possibly unaligned user memory (alignment is a per-rank property, so it must
+// never influence which kernel or how many barriers a rank runs)
+__device__ __forceinline__ uint4 load16_any(const char* p) {
+  const uintptr_t a = (uintptr_t)p;
+  if ((a & 15) == 0) return *reinterpret_cast<const uint4*>(p);
+  uint4 v;
+  if ((a & 3) == 0) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    v = make_uint4(q[0], q[1], q[2], q[3]);
+  } else {
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i >> 2] |= (uint32_t)(uint8_t)p[i] << ((i & 3) * 8);
+    v = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  return v;
+}
+__device__ __forceinline__ void store16_any(char* p, const uint4& v) {
+  const uintptr_t a = (uintptr_t)p;
+  if ((a & 15) == 0) { *reinterpret_cast<uint4*>(p) = v; return; }
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  if ((a & 3) == 0) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(p);
+    q[0] = w[0]; q[1] = w[1]; q[2] = w[2]; q[3] = w[3];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = (char)((w[i >> 2] >> ((i & 3) * 8)) & 0xff);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 bcast_multimem_kernel(CollCtx c, const char* src, char* out, long long nbytes, int root) {
   EpochScope ep(c);
   coll_barrier(c, ep.base + 1);
-  const long long nvec = nbytes >> 4;  // caller guarantees 16-byte multiples and alignment
+  const long long nvec = nbytes >> 4;  // caller guarantees a 16-byte multiple (rank-independent condition)
   const long long per = ceil_div_ll(nvec, gridDim.x);
   const long long lo = min(nvec, (long long)blockIdx.x * per), hi = min(nvec, lo + per);
   if (c.rank == root) {
     uint4* mc = static_cast<uint4*>(c.mc);
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) mc_st_v4(mc + i, *reinterpret_cast<const uint4*>(src + (i << 4)));
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) mc_st_v4(mc + i, load16_any(src + (i << 4)));
   }
   coll_barrier(c, ep.base + 2);
   const uint4* mine = static_cast<const uint4*>(c.data.p[c.rank]);
   if (out != nullptr && (c.rank != root || out != src))
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) *reinterpret_cast<uint4*>(out + (i << 4)) = ld_peer_v4(mine + i);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) store16_any(out + (i << 4), ld_peer_v4(mine + i));
   coll_barrier(c, ep.base + 3);  // nobody reuses staging until every rank has drained it
   ep.commit(c, 3);
 }
@@ -572,20 +602,20 @@ int sdlc_barrier(void* h, int channel, unsigned long long stream) {
 }
 
 // allgather / broadcast / alltoall: pull byte ranges out of the peers' staging buffers
+// `work_bytes` sizes the grid and MUST be identical on every rank (the in-kernel barrier pairs CTA b of
+// every rank): callers pass a rank-independent bound, never their own byte count.
 int sdlc_pull(void* h, int channel, int buf, void* out, const long long* src_off, const long long* nbytes,
-              const long long* dst_off, unsigned long long stream) {
+              const long long* dst_off, long long work_bytes, unsigned long long stream) {
   Comm* c = static_cast<Comm*>(h);
   cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
   const CollCtx ctx = c->make_ctx(channel, buf, 0);
   PullTable t;
-  long long total = 0;
   for (int p = 0; p < kMaxPeers; ++p) {
     t.src_off[p] = p < c->world ? src_off[p] : 0;
     t.nbytes[p] = p < c->world ? nbytes[p] : 0;
     t.dst_off[p] = p < c->world ? dst_off[p] : 0;
-    total += t.nbytes[p];
   }
-  const int blocks = pick_blocks(c, ceil_div_ll(total, 16), kThreads * 4);
+  const int blocks = pick_blocks(c, ceil_div_ll(work_bytes, 16), kThreads * 4);
   pull_kernel<<<blocks, kThreads, 0, s>>>(ctx, static_cast<char*>(out), t);
   LAUNCH_CHECK(c);
   return 0;
@@ -606,8 +636,9 @@ int sdlc_bcast_multimem(void* h, int channel, int buf, const void* src, void* ou
   return 0;
 }
 
+// `work_elems`: rank-independent grid-sizing bound (see sdlc_pull)
 int sdlc_reducescatter(void* h, int channel, int buf, void* out, long long lo, long long cnt, int dtype, int op,
-                       float pre, float post, unsigned long long stream) {
+                       float pre, float post, long long work_elems, unsigned long long stream) {
   Comm* c = static_cast<Comm*>(h);
   cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
   const CollCtx ctx = c->make_ctx(channel, buf, 0);
@@ -615,7 +646,7 @@ int sdlc_reducescatter(void* h, int channel, int buf, void* out, long long lo, l
     op = kSum;
     post /= (float)c->world;
   }
-  const int blocks = pick_blocks(c, cnt, kThreads * 4);
+  const int blocks = pick_blocks(c, work_elems, kThreads * 4);
 #define RS(T) reducescatter_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, static_cast<T*>(out), lo, cnt, op, pre, post)
   switch (dtype) {
     case kF32: RS(float); break;

@@ -18,8 +18,8 @@ using namespace sdlc;
 
 extern "C" {
 int sdlc_allreduce(void*, int, int, long long, long long, int, int, float, float, int, unsigned long long);
-int sdlc_pull(void*, int, int, void*, const long long*, const long long*, const long long*, unsigned long long);
-int sdlc_reducescatter(void*, int, int, void*, long long, long long, int, int, float, float, unsigned long long);
+int sdlc_pull(void*, int, int, void*, const long long*, const long long*, const long long*, long long, unsigned long long);
+int sdlc_reducescatter(void*, int, int, void*, long long, long long, int, int, float, float, long long, unsigned long long);
 int sdlc_pack(void*, int, const unsigned long long*, const long long*, const long long*, int, int, unsigned long long);
 int sdlc_bcast_multimem(void*, int, int, const void*, void*, long long, int, unsigned long long);
 }
@@ -98,7 +98,7 @@ int exec_broadcast(Comm* c, const sdl::GpuWork* w, unsigned long long s, const F
   const bool mc = c->bufs[buf].mc != nullptr && c->use_mc && c->world > 1;
   for (long long b0 = 0; b0 < total || b0 == 0; b0 += cap) {
     const long long nb = std::min(cap, total - b0);
-    if (mc && (nb & 15) == 0 && (((uintptr_t)(user + b0)) & 15) == 0) {
+    if (mc && (nb & 15) == 0) {   // rank-independent choice: every rank must run the same kernel
       if (sdlc_bcast_multimem(c, 0, buf, user + b0, user + b0, nb, w->root, s)) return fail(c, "bcast_multimem");
     } else {
       if (c->rank == w->root) {
@@ -108,7 +108,7 @@ int exec_broadcast(Comm* c, const sdl::GpuWork* w, unsigned long long s, const F
       }
       long long so[kMaxPeers] = {0}, nn[kMaxPeers] = {0}, dof[kMaxPeers] = {0};
       if (c->rank != w->root) nn[w->root] = nb;
-      if (sdlc_pull(c, 0, buf, user + b0, so, nn, dof, s)) return fail(c, "pull");
+      if (sdlc_pull(c, 0, buf, user + b0, so, nn, dof, nb, s)) return fail(c, "pull");
     }
     if (total == 0) break;
   }
@@ -133,12 +133,13 @@ int exec_allgather(Comm* c, const sdl::GpuWork* w, unsigned long long s, const F
       long long off = 0, n = mine;
       if (sdlc_pack(c, buf, &p, &off, &n, 1, 1, s)) return fail(c, "pack");
     }
-    long long so[kMaxPeers] = {0}, nn[kMaxPeers] = {0}, dof[kMaxPeers] = {0};
+    long long so[kMaxPeers] = {0}, nn[kMaxPeers] = {0}, dof[kMaxPeers] = {0}, work = 0;
     for (int p = 0; p < c->world; ++p) {
       nn[p] = std::max(0ll, std::min(cap, bytes[p] - b0));
       dof[p] = prefix[p] + b0;
+      work += nn[p];
     }
-    if (sdlc_pull(c, 0, buf, w->out[0], so, nn, dof, s)) return fail(c, "pull");
+    if (sdlc_pull(c, 0, buf, w->out[0], so, nn, dof, work, s)) return fail(c, "pull");
     if (maxb == 0) break;
   }
   return 0;
@@ -178,7 +179,14 @@ int exec_alltoall(Comm* c, const sdl::GpuWork* w, unsigned long long s, const Fa
       nn[p] = std::max(0ll, std::min(segcap, seg - b0));
       dof[p] = recv_prefix[p] + b0;
     }
-    if (sdlc_pull(c, 0, buf, w->out[0], so, nn, dof, s)) return fail(c, "pull");
+    // grid bound = the largest receive volume of any rank in this round (same value everywhere)
+    long long work = 0;
+    for (int d = 0; d < W; ++d) {
+      long long recv_d = 0;
+      for (int p = 0; p < W; ++p) recv_d += std::max(0ll, std::min(segcap, (long long)w->splits[p * st + d] * row - b0));
+      work = std::max(work, recv_d);
+    }
+    if (sdlc_pull(c, 0, buf, w->out[0], so, nn, dof, work, s)) return fail(c, "pull");
     if (maxseg == 0) break;
   }
   return 0;
@@ -201,7 +209,7 @@ int exec_reducescatter(Comm* c, const sdl::GpuWork* w, unsigned long long s, con
     const long long cnt = std::max(0ll, hi - lo);
     char* out = static_cast<char*>(w->out[0]) + (cnt > 0 ? (lo - my_lo) * esz : 0);
     if (sdlc_reducescatter(c, 0, buf, out, cnt > 0 ? lo - e0 : 0, cnt, (int)w->dtype, (int)w->op, (float)w->prescale,
-                           (float)w->postscale, s))
+                           (float)w->postscale, (ne + W - 1) / W, s))
       return fail(c, "reducescatter");
     if (total == 0) break;
   }

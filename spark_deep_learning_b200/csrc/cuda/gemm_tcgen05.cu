@@ -1,0 +1,363 @@
+// bf16 GEMM on the 5th-generation tensor cores with a fused epilogue, hand-written for sm_100a:
+//
+//     Y[M,N] = epilogue( X[M,K] . W[N,K]^T + bias[N] )        epilogue: none | GELU (tanh or erf)
+//
+// (exactly torch.nn.functional.linear; this is the forward of every BERT-large projection,
+// BASELINE.json config 3.)  Structure (blackwell_cuda_programming.md "Anatomy"):
+//
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d  global -> 128B-swizzled smem ring (kStages)
+//   warp 1   MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 x N x K16),
+//                           accumulators live in TMEM; tcgen05.commit frees smem slots / publishes tiles
+//   warp 2   TMEM allocator tcgen05.alloc of 2 x BLOCK_N fp32 columns (double-buffered accumulator)
+//   warps 4-7 epilogue      tcgen05.ld 32x32b.x32 -> +bias -> GELU -> bf16 -> 16-byte global stores,
+//                           overlapped with the MMA of the next tile (tmem_full / tmem_empty barriers)
+//
+// Persistent: grid = min(#SMs, #tiles); every role walks the same static tile schedule.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;      // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kNumThreads = 256; // 8 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int kEpiWarp0 = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem]^T ; both operands K-major, swizzle-128B
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//  [0,14) start address >> 4, [16,30) LBO >> 4 (=1, unused for swizzled K-major), [32,46) SBO >> 4
+//  (8 rows x 128 B = 1024 B between 8-row groups), [46,48) version = 1 (sm_100), [61,64) layout = 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format BF16 (1) at
+// [7,10)/[10,13), a/b major K (0) at 15/16, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * fmaf(k1 * x * x, x, x);
+  // tanh(u) = 1 - 2 / (exp(2u) + 1)
+  const float t = 1.f - 2.f / (__expf(2.f * u) + 1.f);
+  return 0.5f * x * (1.f + t);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+};
+
+// epilogue: 0 none, 1 GELU(tanh), 2 GELU(erf).  pre_act (optional) receives X.W^T + bias before the
+// activation (needed by the backward of GELU).
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pre_act, const float* __restrict__ bias,
+                 int M, int N, int K, int epilogue) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using L = SmemLayout<BLOCK_N>;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * L::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint64_t* full = bars;                    // [kStages]
+  uint64_t* empty = bars + kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // power of two: 256 or 512
+
+  if (warp == 0 && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], L::kStageBytes);
+          tma_load_2d(smem_a + stage * L::kABytes, &map_a, &full[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(smem_b + stage * L::kBBytes, &map_b, &full[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);              // TMA bytes have landed
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * L::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * L::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
+            const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
+            umma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                 // frees the smem slot when these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue: TMEM -> registers -> bias / GELU -> bf16 -> global =====
+    const int ew = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + ew * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int col0 = n_blk * BLOCK_N + c0;
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < N) {           // N % 8 == 0 is required by the host wrapper
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]) + (bias ? __ldg(bias + col0 + j + i) : 0.f);
+              if (pre_act) {
+                uint4 p;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                p.x = *reinterpret_cast<uint32_t*>(&h0); p.y = *reinterpret_cast<uint32_t*>(&h1);
+                p.z = *reinterpret_cast<uint32_t*>(&h2); p.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(pre_act + (size_t)row * N + col0 + j) = p;
+              }
+              if (epilogue == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = gelu_tanh(f[i]);
+              } else if (epilogue == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
+              }
+              uint4 o;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+              o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+              o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(out + (size_t)row * N + col0 + j) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static bool load_encode() {
+  if (g_encode) return true;
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) != cudaSuccess || !fp) {
+    cudaGetLastError();
+    return false;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fp);
+  return true;
+}
+
+// row-major [rows, cols] bf16 matrix, box = [box_rows, 64 cols], 128-byte swizzle
+static bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace gemm
+
+using namespace gemm;
+
+extern "C" {
+
+// Y[M,N] = act(X[M,K] . W[N,K]^T + bias).  Requirements: K % 8 == 0, N % 8 == 0, 16-byte aligned pointers.
+// Returns 0 on success, negative on error.
+int sdlc_gemm_bf16(const void* x, const void* w, const float* bias, void* out, void* pre_act, int M, int N, int K,
+                   int epilogue, int block_n, int num_sms, unsigned long long stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((K % 8) != 0 || (N % 8) != 0) return -2;
+  if (!load_encode()) return -3;
+  CUtensorMap ma, mb;
+  if (block_n != 256) block_n = 128;
+  if (!make_map(&ma, x, (uint64_t)M, (uint64_t)K, BLOCK_M)) return -4;
+  if (!make_map(&mb, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n)) return -4;
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+  if (num_sms <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (block_n == 256) {
+    const int smem = SmemLayout<256>::kTotal;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    gemm_bf16_kernel<256><<<grid, kNumThreads, smem, s>>>(ma, mb, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(pre_act), bias, M, N, K, epilogue);
+  } else {
+    const int smem = SmemLayout<128>::kTotal;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    gemm_bf16_kernel<128><<<grid, kNumThreads, smem, s>>>(ma, mb, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(pre_act), bias, M, N, K, epilogue);
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1;
+}
+
+}  // extern "C"

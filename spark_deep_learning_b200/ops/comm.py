@@ -84,9 +84,9 @@ def load():
         "sdlc_wire_bytes": (i64, [i64, i32]),
         "sdlc_allreduce_wire": (i32, [vp, i32, vp, i64, i32, i32, i32, i64, f32, f32, u64]),
         "sdlc_barrier": (i32, [vp, i32, u64]),
-        "sdlc_pull": (i32, [vp, i32, i32, vp, P(i64), P(i64), P(i64), u64]),
+        "sdlc_pull": (i32, [vp, i32, i32, vp, P(i64), P(i64), P(i64), i64, u64]),
         "sdlc_bcast_multimem": (i32, [vp, i32, i32, vp, vp, i64, i32, u64]),
-        "sdlc_reducescatter": (i32, [vp, i32, i32, vp, i64, i64, i32, i32, f32, f32, u64]),
+        "sdlc_reducescatter": (i32, [vp, i32, i32, vp, i64, i64, i32, i32, f32, f32, i64, u64]),
         "sdlc_pack": (i32, [vp, i32, P(u64), P(i64), P(i64), i32, i32, u64]),
         "sdlc_scale": (i32, [vp, vp, i64, i32, f32, u64]),
         "sdlc_fused_step": (i32, [vp, i32, i32, i32, i64, i32, vp, vp, vp, f32, P(f32), u64]),

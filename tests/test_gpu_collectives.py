@@ -140,7 +140,7 @@ def test_pull_allgather_and_alltoall(lib):
     nb = A(*[rows[p] * row_bytes if p < world else 0 for p in range(8)])
     pre = [sum(rows[:p]) * row_bytes for p in range(world)] + [0] * (8 - world)
     _launch_all(vg, lambda r, c, s: lib.sdlc_pull(c._h, 0, st[r].id, ctypes.c_void_p(outs[r].data_ptr()),
-                                                 A(*[0] * 8), nb, A(*pre), s))
+                                                 A(*[0] * 8), nb, A(*pre), sum(rows) * row_bytes, s))
     ref = torch.cat([(torch.arange(rows[p] * row_bytes) % 251 + p).to(torch.uint8) for p in range(world)]).cuda()
     for o in outs:
         assert torch.equal(o, ref)
@@ -159,7 +159,7 @@ def test_reducescatter(lib, dtype):
     outs = [torch.zeros(cnts[r], dtype=dtype, device="cuda") for r in range(world)]
     torch.cuda.synchronize()
     _launch_all(vg, lambda r, c, s: lib.sdlc_reducescatter(
-        c._h, 0, st[r].id, ctypes.c_void_p(outs[r].data_ptr()), los[r], cnts[r], DT[dtype], 0, 1.0, 1.0, s))
+        c._h, 0, st[r].id, ctypes.c_void_p(outs[r].data_ptr()), los[r], cnts[r], DT[dtype], 0, 1.0, 1.0, 1003, s))
     tol = 1e-5 if dtype == torch.float32 else 3e-2
     for r in range(world):
         assert torch.allclose(outs[r].float(), ref[los[r]:los[r] + cnts[r]], rtol=tol, atol=tol * 4)
