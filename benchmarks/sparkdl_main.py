@@ -39,10 +39,10 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
     crit = torch.nn.CrossEntropyLoss()
 
     def fwd(x, y):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            if model_name == "resnet50":
+        if model_name == "resnet50":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
                 return crit(model(x.contiguous(memory_format=torch.channels_last)), y)
-            return model(x, labels=y)
+        return model(x, labels=y)          # bf16 parameters, fp32 master weights in the fused optimizer
 
     dx, dy = host_x.to(dev), host_y.to(dev)
 

@@ -135,7 +135,9 @@ int sdlc_gbdt_hist(const void* bins, const void* gh, const void* pos, void* hist
 int sdlc_gbdt_hist_allreduce(void* h, int channel, int buf, const void* bins, const void* gh, const void* pos, long long n,
                              int F, long long hist_elems, void* grid_ctr, unsigned int grid_epoch, unsigned long long stream) {
   Comm* c = static_cast<Comm*>(h);
-  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  // the caller's stream as given (0 = the legacy default stream): the launch must stay ordered with the
+  // memset before it and the reads after it
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const CollCtx ctx = c->make_ctx(channel, buf, 0);
   // every CTA must be co-resident (device-local barrier): at most one CTA per SM, bounded by kMaxBlocks
   int blocks = c->max_blocks * 4;

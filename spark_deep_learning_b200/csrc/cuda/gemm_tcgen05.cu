@@ -319,6 +319,39 @@ static bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t 
   return r == CUDA_SUCCESS;
 }
 
+// dX_pre = dY * gelu'(pre) for the backward of the fused bias+GELU epilogue (one streaming pass, bf16x8)
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out,
+                long long nvec, int kind) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = reinterpret_cast<const uint4*>(dy)[v], b = reinterpret_cast<const uint4*>(pre)[v];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float g[2] = {__uint_as_float(aw[i] << 16), __uint_as_float(aw[i] & 0xffff0000u)};
+      const float z[2] = {__uint_as_float(bw[i] << 16), __uint_as_float(bw[i] & 0xffff0000u)};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float d;
+        if (kind == 1) {
+          const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+          const float u = k0 * fmaf(k1 * z[j] * z[j], z[j], z[j]);
+          const float t = 1.f - 2.f / (__expf(2.f * u) + 1.f);
+          d = 0.5f * (1.f + t) + 0.5f * z[j] * (1.f - t * t) * k0 * (1.f + 3.f * k1 * z[j] * z[j]);
+        } else {
+          const float cdf = 0.5f * (1.f + erff(z[j] * 0.7071067811865476f));
+          d = cdf + z[j] * __expf(-0.5f * z[j] * z[j]) * 0.3989422804014327f;
+        }
+        g[j] *= d;
+      }
+      __nv_bfloat162 h = __floats2bfloat162_rn(g[0], g[1]);
+      ow[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(out)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
 }  // namespace gemm
 
 using namespace gemm;
@@ -358,6 +391,17 @@ int sdlc_gemm_bf16(const void* x, const void* w, const float* bias, void* out, v
   }
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1;
+}
+
+// out = dy * gelu'(pre); numel % 8 == 0.  kind: 1 tanh, 2 erf
+int sdlc_gelu_bwd(const void* dy, const void* pre, void* out, long long numel, int kind, unsigned long long stream) {
+  const long long nvec = numel / 8;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  gelu_bwd_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(pre), static_cast<__nv_bfloat16*>(out), nvec, kind);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 }  // extern "C"

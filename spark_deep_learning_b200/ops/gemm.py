@@ -24,6 +24,8 @@ def _lib():
         vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong
         lib.sdlc_gemm_bf16.restype = i32
         lib.sdlc_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, u64]
+        lib.sdlc_gelu_bwd.restype = i32
+        lib.sdlc_gelu_bwd.argtypes = [vp, vp, vp, ctypes.c_longlong, i32, u64]
         _sig = True
     return lib
 
@@ -76,19 +78,17 @@ class _LinearAct(torch.autograd.Function):
         x2d, weight, pre = ctx.saved_tensors
         dy2d = dy.reshape(-1, dy.shape[-1])
         if pre is not None:
-            z = pre.float()
-            if ctx.act == "gelu_tanh":
-                k0, k1 = 0.7978845608028654, 0.044715
-                u = k0 * (z + k1 * z ** 3)
-                t = torch.tanh(u)
-                dg = 0.5 * (1 + t) + 0.5 * z * (1 - t * t) * k0 * (1 + 3 * k1 * z * z)
-            else:
-                cdf = 0.5 * (1 + torch.erf(z * 0.7071067811865476))
-                dg = cdf + z * torch.exp(-0.5 * z * z) * 0.3989422804014327
-            dy2d = (dy2d.float() * dg).to(torch.bfloat16)
+            dy2d = dy2d.contiguous()
+            g = torch.empty_like(pre)
+            rc = _lib().sdlc_gelu_bwd(_p(dy2d), _p(pre), _p(g), pre.numel(), 1 if ctx.act == "gelu_tanh" else 2,
+                                      torch.cuda.current_stream(pre.device).cuda_stream)
+            if rc != 0:
+                raise RuntimeError("sdlc_gelu_bwd failed")
+            launch_counter.add(1)
+            dy2d = g
         dx = dy2d @ weight                                   # dgrad: plain library GEMM
         dw = dy2d.t() @ x2d                                  # wgrad: plain library GEMM
-        db = dy2d.float().sum(0) if ctx.has_bias else None
+        db = dy2d.sum(0, dtype=torch.float32) if ctx.has_bias else None
         return dx.view(ctx.x_shape), dw, db, None
 
 
