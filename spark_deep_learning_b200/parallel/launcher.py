@@ -174,6 +174,8 @@ def launch_gang(main, kwargs, num_proc, stream_all_logs, extra_env=None):
             # make this package importable in the worker even when it is not installed
             root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
             env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+            if os.environ.get("SPARKDL_HOROVOD_SHIM") == "1":
+                env["PYTHONPATH"] = os.path.join(root, "spark_deep_learning_b200", "compat") + os.pathsep + env["PYTHONPATH"]
             if extra_env:
                 env.update(extra_env)
             p = subprocess.Popen(

@@ -141,3 +141,17 @@ def test_distributed_cpu_workers_match_single_worker(monkeypatch):
     assert np.allclose(single, dist, atol=1e-4), np.abs(single - dist).max()
     with pytest.raises(ValueError, match="distributed"):
         XgboostRegressor(num_workers=2, baseMarginCol="label").fit(df)
+
+
+def test_pipeline_and_cross_validator():
+    """ref xgboost.py:168-169: usable in Pipeline and CrossValidator (copy / param maps)."""
+    from spark_deep_learning_b200.xgboost.ml import (CrossValidator, ParamGridBuilder, Pipeline,
+                                                     RegressionEvaluator)
+    X, y = _toy(900, f=5, nan_frac=0.0)
+    df = pd.DataFrame({"features": list(X), "label": y})
+    reg = XgboostRegressor(n_estimators=15, learning_rate=0.3)
+    grid = ParamGridBuilder().addGrid(reg.max_depth, [1, 4]).build()
+    cv = CrossValidator(reg, grid, RegressionEvaluator(), numFolds=2).fit(df)
+    assert cv.bestIndex == 1 and cv.avgMetrics[1] < cv.avgMetrics[0]
+    out = Pipeline([reg]).fit(df).transform(df)
+    assert "prediction" in out.columns
