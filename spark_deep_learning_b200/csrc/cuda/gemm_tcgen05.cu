@@ -26,9 +26,10 @@ namespace gemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
-constexpr int kNumThreads = 256; // 8 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int kNumThreads = 384; // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;     // two warps per TMEM lane quarter, each owning half of the columns
+template <int BLOCK_N> struct Stages { static constexpr int value = BLOCK_N == 256 ? 4 : 6; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,10 +112,19 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float t = 1.f - 2.f / (__expf(2.f * u) + 1.f);
   return 0.5f * x * (1.f + t);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution): one MUFU.EX2 + one MUFU.RCP
+__device__ __forceinline__ float fast_erf(float z) {
+  const float a = fabsf(z);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, a, 1.f));
+  const float p = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float r = 1.f - p * __expf(-a * a);
+  return copysignf(r, z);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + fast_erf(x * 0.7071067811865476f)); }
 
 template <int BLOCK_N>
 struct SmemLayout {
+  static constexpr int kStages = Stages<BLOCK_N>::value;
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -131,6 +141,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = SmemLayout<BLOCK_N>;
+  constexpr int kStages = L::kStages;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * L::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
@@ -157,7 +168,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], kEpiWarps);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,18 +230,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> bias / GELU -> bf16 -> global =====
-    const int ew = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    const int q = (warp - kEpiWarp0) & 3;            // == warp % 4: TMEM lanes [32q, 32q+32)
+    const int half = (warp - kEpiWarp0) >> 2;        // which half of the tile's columns this warp drains
+    constexpr int kColsPerWarp = BLOCK_N / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + ew * 32 + lane;
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -248,7 +261,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (col0 + j < N) {           // N % 8 == 0 is required by the host wrapper
               float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]) + (bias ? __ldg(bias + col0 + j + i) : 0.f);
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
+              if (bias) {                 // two 16-byte loads instead of eight scalar ones
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
               if (pre_act) {
                 uint4 p;
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -340,7 +359,7 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
           const float t = 1.f - 2.f / (__expf(2.f * u) + 1.f);
           d = 0.5f * (1.f + t) + 0.5f * z[j] * (1.f - t * t) * k0 * (1.f + 3.f * k1 * z[j] * z[j]);
         } else {
-          const float cdf = 0.5f * (1.f + erff(z[j] * 0.7071067811865476f));
+          const float cdf = 0.5f * (1.f + fast_erf(z[j] * 0.7071067811865476f));
           d = cdf + z[j] * __expf(-0.5f * z[j] * z[j]) * 0.3989422804014327f;
         }
         g[j] *= d;

@@ -82,6 +82,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                              % ", ".join(str(i) for i in sorted(all_ids - named_ids)))
         self._names = {id(p): n for n, p in named_parameters}
         self._passes = {}
+        self._grad_ptr = {}
         self._buckets = []
         self._bucket_of = {}
         self._next_launch = 0
@@ -135,6 +136,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                     view.copy_(p.grad)
                 p.grad = view
                 self._bucket_of[id(p)] = (b, off)
+                self._grad_ptr[id(p)] = view.data_ptr()
                 self._passes[id(p)] = 0
                 if b.pflat is not None:
                     pv = b.pflat[off:off + p.numel()].view_as(p)
@@ -153,23 +155,31 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook()))
 
     def _make_hook(self):
+        # Runs on the autograd thread once per parameter per backward: keep it to a pointer compare and
+        # a counter (a launch-bound model such as BERT-large has ~400 of these on its critical path).
+        passes = self._passes
+        bucket_of = self._bucket_of
+        expected = self._grad_ptr
+
         def hook(p):
-            b, off = self._bucket_of[id(p)]
+            pid = id(p)
+            b, off = bucket_of[pid]
             if b.launched:
                 raise AssertionError(
                     "Gradients were computed more than backward_passes_per_step times before call "
                     "to step(). Increase backward_passes_per_step to accumulate gradients locally.")
-            view = b.flat[off:off + p.numel()].view_as(p)
             g = p.grad
             if g is None:
                 return
-            if g.data_ptr() != view.data_ptr():
+            if g.data_ptr() != expected[pid]:
                 # someone replaced .grad (zero_grad(set_to_none=True), an AMP unscale copy ...):
                 # fold it back into the bucket and re-alias
+                view = b.flat[off:off + p.numel()].view_as(p)
                 view.copy_(g)
                 p.grad = view
-            self._passes[id(p)] += 1
-            if self._passes[id(p)] == self.backward_passes_per_step:
+            n = passes[pid] + 1
+            passes[pid] = n
+            if n == self.backward_passes_per_step:
                 b.pending -= 1
                 if b.pending == 0:
                     self._launch_ready()
@@ -290,10 +300,16 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         if not self._buckets:
             return super(self.__class__, self).zero_grad(set_to_none=set_to_none)
         for b in self._buckets:
-            b.flat.zero_()
-            for p, off in zip(b.params, b.offsets):
-                if p.grad is None or p.grad.data_ptr() != b.flat.data_ptr() + off * b.flat.element_size():
-                    p.grad = b.flat[off:off + p.numel()].view_as(p)
+            b.flat.zero_()                     # one memset per bucket; a replaced / dropped .grad is re-aliased lazily
+            if set_to_none is None:            # (never true: placeholder keeps the signature honest)
+                continue
+        self._zero_calls = getattr(self, "_zero_calls", 0) + 1
+        if self._zero_calls <= 2 or self._zero_calls % 64 == 0:
+            # periodic full check that every .grad still aliases its bucket (cheap insurance, off the hot path)
+            for b in self._buckets:
+                for p, off in zip(b.params, b.offsets):
+                    if p.grad is None or p.grad.data_ptr() != self._grad_ptr[id(p)]:
+                        p.grad = b.flat[off:off + p.numel()].view_as(p)
         bucketed = set(self._bucket_of)
         for g in self.param_groups:
             for p in g["params"]:
