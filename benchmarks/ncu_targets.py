@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Small single-GPU drivers for `ncu` captures of our top kernels (B200_PROFILING.md recipe).
+usage: python benchmarks/ncu_targets.py gemm|bn|allreduce|fused_step"""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+
+def gemm():
+    from spark_deep_learning_b200.ops import gemm as g
+    m, n, k = 8192, 4096, 4096
+    x = torch.randn(m, k, device="cuda").bfloat16()
+    w = torch.randn(n, k, device="cuda").bfloat16()
+    b = torch.randn(n, device="cuda")
+    for _ in range(6):
+        g.gemm_bf16(x, w, b, "gelu", block_n=256)
+    # BERT FFN-up shape (tokens 8192, 1024 -> 4096)
+    x2 = torch.randn(8192, 1024, device="cuda").bfloat16()
+    w2 = torch.randn(4096, 1024, device="cuda").bfloat16()
+    for _ in range(6):
+        g.gemm_bf16(x2, w2, b, "gelu", block_n=256)
+    torch.cuda.synchronize()
+
+
+def bn():
+    from spark_deep_learning_b200.ops import norm
+    x = torch.randn(256, 256, 56, 56, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    r = torch.randn(256, 256, 56, 56, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    m = torch.nn.BatchNorm2d(256).cuda()
+    for _ in range(5):
+        y = norm.batch_norm_act(x, m, r, True)
+        y.backward(torch.ones_like(y))
+    torch.cuda.synchronize()
+
+
+def _vg():
+    from spark_deep_learning_b200.ops.comm import VirtualGroup
+    from spark_deep_learning_b200.utils.config import get_config
+    return VirtualGroup(1, get_config(refresh=True), max_blocks=32)
+
+
+def allreduce():
+    vg = _vg()
+    lib = vg.comms[0]._lib
+    n = 64 << 20
+    buf = vg.alloc(n * 4)[0]
+    buf.tensor(torch.float32, n).fill_(1.0)
+    torch.cuda.synchronize()
+    s = vg.streams[0].cuda_stream
+    for _ in range(5):
+        lib.sdlc_allreduce(vg.comms[0]._h, 1, buf.id, 0, n, 6, 0, 1.0, 1.0, 2, s)
+    torch.cuda.synchronize()
+
+
+def fused_step():
+    vg = _vg()
+    c = vg.comms[0]
+    lib = c._lib
+    n = 32 << 20
+    g, p = vg.alloc(n * 4)[0], vg.alloc(n * 4)[0]
+    ns = lib.sdlc_fused_state_elems(c._h, n, 6)
+    s1, s2 = torch.zeros(ns, device="cuda"), torch.zeros(ns, device="cuda")
+    args = (ctypes.c_float * 16)(*([2, 1e-3, 0.01, 0, 0, 0, 0, 0.9, 0.999, 1e-8, 0.1, 0.001] + [0.0] * 4))
+    s = vg.streams[0].cuda_stream
+    for _ in range(5):
+        lib.sdlc_fused_step(c._h, 1, g.id, p.id, n, 6, ctypes.c_void_p(s1.data_ptr()), ctypes.c_void_p(s2.data_ptr()), None, 1.0, args, s)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    {"gemm": gemm, "bn": bn, "allreduce": allreduce, "fused_step": fused_step}[sys.argv[1]]()

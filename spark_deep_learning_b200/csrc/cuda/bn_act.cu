@@ -121,9 +121,9 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long 
 }
 
 // ---------------- finalize: mean / rstd / fused scale+shift, running statistics ----------------------
-// Block = 32 channels x 8 row groups: the per-block partials are summed by 8 threads per channel
+// Block = 32 channels x 32 row groups: the per-block partials are summed by 32 threads per channel
 // (coalesced 128-byte rows), then combined through shared memory in a fixed order (deterministic).
-constexpr int kFinX = 32, kFinY = 8;
+constexpr int kFinX = 32, kFinY = 32;   // 1024 threads: the partial-row loop is latency bound, so go wide
 
 __device__ __forceinline__ void sum_partials(const float* __restrict__ partial, int nblocks, int C, int c, float& s, float& q) {
   __shared__ float sh[2][kFinY][kFinX];
@@ -233,26 +233,22 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restric
   }
 }
 
-// ---------------- backward pass 1: partial sum(dz), sum(dz * xhat) ----------------------------------------
+// ---------------- backward pass 1: partial sum(dz), sum(dz * x) -------------------------------------------
+// (sum(dz * xhat) = rstd * (sum(dz*x) - mean * sum(dz)) is formed in the finalize kernel: the streaming
+// loop keeps no per-channel constants in registers, which buys occupancy.)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ partial,
-                     long long nvec, int C, int relu) {
+                     float* __restrict__ partial, long long nvec, int C, int relu) {
   constexpr int N = V<T>::N;
   const int CV = C / N;
   extern __shared__ float smem[];
   const long long T_all = (long long)gridDim.x * kThreads;
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int cvv = (int)(g % CV);
-  float mu[N], rs[N], acc[2 * N];
+  float acc[2 * N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    mu[i] = mean[cvv * N + i];
-    rs[i] = rstd[cvv * N + i];
-    acc[i] = 0.f;
-    acc[N + i] = 0.f;
-  }
+  for (int i = 0; i < 2 * N; ++i) acc[i] = 0.f;
   for (long long v0 = g; v0 < nvec; v0 += 2 * T_all) {
     const long long v1 = v0 + T_all;
     const bool h1 = v1 < nvec;
@@ -269,14 +265,14 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const ui
     for (int i = 0; i < N; ++i) {
       const float dz = (m0 >> i) & 1u ? d0[i] : 0.f;
       acc[i] += dz;
-      acc[N + i] = fmaf(dz, (f0[i] - mu[i]) * rs[i], acc[N + i]);
+      acc[N + i] = fmaf(dz, f0[i], acc[N + i]);
     }
     if (h1) {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         const float dz = (m1 >> i) & 1u ? d1[i] : 0.f;
         acc[i] += dz;
-        acc[N + i] = fmaf(dz, (f1[i] - mu[i]) * rs[i], acc[N + i]);
+        acc[N + i] = fmaf(dz, f1[i], acc[N + i]);
       }
     }
   }
@@ -293,41 +289,42 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const ui
 
 __global__ void __launch_bounds__(kFinX * kFinY)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, float inv_m,
-                       const float* __restrict__ weight, const float* __restrict__ rstd,
+                       const float* __restrict__ weight, const float* __restrict__ mean, const float* __restrict__ rstd,
                        float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ c0,
                        float* __restrict__ c1, float* __restrict__ c2) {
   const int c = blockIdx.x * kFinX + threadIdx.x;
   float s, q;
   sum_partials(partial, nblocks, C, c, s, q);
   if (c >= C || threadIdx.y != 0) return;
+  const float mu = mean[c], rs = rstd[c];
+  const float dgamma = rs * (q - mu * s);      // sum(dz * xhat)
   dbias[c] = s;
-  dweight[c] = q;
-  const float a = (weight ? weight[c] : 1.f) * rstd[c];
-  c0[c] = a;             // dx = c0 * (dz - c1 - xhat * c2)
-  c1[c] = s * inv_m;
-  c2[c] = q * inv_m;
+  dweight[c] = dgamma;
+  // dx = a*(dz - s/M - xhat*dgamma/M)  with a = gamma*rstd, xhat = (x-mu)*rs   ==>   dx = A*dz + B*x + D
+  const float a = (weight ? weight[c] : 1.f) * rs;
+  const float k2 = dgamma * inv_m * rs;
+  c0[c] = a;
+  c1[c] = -a * k2;
+  c2[c] = a * (k2 * mu - s * inv_m);
 }
 
-// ---------------- backward pass 2: dx (and dz for the residual branch) -----------------------------------
+// ---------------- backward pass 2: dx = A*dz + B*x + D (and dz for the residual branch) -------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask,
-                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ c0,
-                    const float* __restrict__ c1, const float* __restrict__ c2, T* __restrict__ dx, T* __restrict__ dz_out,
-                    long long nvec, int C, int relu) {
+                    const float* __restrict__ c0, const float* __restrict__ c1, const float* __restrict__ c2,
+                    T* __restrict__ dx, T* __restrict__ dz_out, long long nvec, int C, int relu) {
   constexpr int N = V<T>::N;
   const int CV = C / N;
   const long long T_all = (long long)gridDim.x * kThreads;
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int cv = (int)(g % CV);
-  float mu[N], rs[N], k0[N], k1[N], k2[N];
+  float A[N], B[N], D[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    mu[i] = mean[cv * N + i];
-    rs[i] = rstd[cv * N + i];
-    k0[i] = c0[cv * N + i];
-    k1[i] = c1[cv * N + i];
-    k2[i] = c2[cv * N + i];
+    A[i] = c0[cv * N + i];
+    B[i] = c1[cv * N + i];
+    D[i] = c2[cv * N + i];
   }
   for (long long v0 = g; v0 < nvec; v0 += 2 * T_all) {
     const long long v1 = v0 + T_all;
@@ -345,7 +342,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uin
     for (int i = 0; i < N; ++i) {
       const float dz = (m0 >> i) & 1u ? d0[i] : 0.f;
       d0[i] = dz;
-      f0[i] = k0[i] * (dz - k1[i] - (f0[i] - mu[i]) * rs[i] * k2[i]);
+      f0[i] = fmaf(A[i], dz, fmaf(B[i], f0[i], D[i]));
     }
     V<T>::store(dx + v0 * N, f0);
     if (dz_out) V<T>::store(dz_out + v0 * N, d0);
@@ -354,7 +351,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uin
       for (int i = 0; i < N; ++i) {
         const float dz = (m1 >> i) & 1u ? d1[i] : 0.f;
         d1[i] = dz;
-        f1[i] = k0[i] * (dz - k1[i] - (f1[i] - mu[i]) * rs[i] * k2[i]);
+        f1[i] = fmaf(A[i], dz, fmaf(B[i], f1[i], D[i]));
       }
       V<T>::store(dx + v1 * N, f1);
       if (dz_out) V<T>::store(dz_out + v1 * N, d1);
@@ -427,18 +424,18 @@ int sdlc_bn_bwd(const void* dy, const void* x, const void* mask, const float* we
   if (cv > kThreads) cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * 2 * c, s);
   if (dtype == 5)
     bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
-                                                                    static_cast<const uint8_t*>(mask), mean, rstd, partial, nvec, c, relu);
+                                                                    static_cast<const uint8_t*>(mask), partial, nvec, c, relu);
   else
     bn_bwd_reduce_kernel<float><<<grid, kThreads, smem, s>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
-                                                            static_cast<const uint8_t*>(mask), mean, rstd, partial, nvec, c, relu);
-  bn_bwd_finalize_kernel<<<(c + kFinX - 1) / kFinX, dim3(kFinX, kFinY), 0, s>>>(partial, grid, c, 1.f / (float)m, weight, rstd, dweight, dbias, c0, c1, c2);
+                                                            static_cast<const uint8_t*>(mask), partial, nvec, c, relu);
+  bn_bwd_finalize_kernel<<<(c + kFinX - 1) / kFinX, dim3(kFinX, kFinY), 0, s>>>(partial, grid, c, 1.f / (float)m, weight, mean, rstd, dweight, dbias, c0, c1, c2);
   if (dtype == 5)
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
-                                                                static_cast<const uint8_t*>(mask), mean, rstd, c0, c1, c2,
+                                                                static_cast<const uint8_t*>(mask), c0, c1, c2,
                                                                 static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dz), nvec, c, relu);
   else
     bn_bwd_apply_kernel<float><<<grid, kThreads, 0, s>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
-                                                        static_cast<const uint8_t*>(mask), mean, rstd, c0, c1, c2, static_cast<float*>(dx),
+                                                        static_cast<const uint8_t*>(mask), c0, c1, c2, static_cast<float*>(dx),
                                                         static_cast<float*>(dz), nvec, c, relu);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

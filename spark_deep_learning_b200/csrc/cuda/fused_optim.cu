@@ -29,6 +29,52 @@ template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<__nv_bfloat16>(const
 template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<__half>(const void* p) { return mc_ld_reduce_f16(p); }
 
 template <typename T>
+__device__ __forceinline__ void optimizer_update(float* gr, float* pw, float* __restrict__ s1, float* __restrict__ s2,
+                                                 long long k0, float scale, const OptimArgs& a) {
+  using Tr = VecTraits<T>;
+  float m1[Tr::N], m2[Tr::N];
+  if (a.kind != 0 || a.momentum != 0.f) {
+#pragma unroll
+    for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(m1 + i) = *reinterpret_cast<const float4*>(s1 + k0 + i);
+  }
+  if (a.kind != 0) {
+#pragma unroll
+    for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(m2 + i) = *reinterpret_cast<const float4*>(s2 + k0 + i);
+  }
+#pragma unroll
+  for (int i = 0; i < Tr::N; ++i) {
+    float gi = gr[i] * scale, p = pw[i];
+    if (a.kind == 0) {
+      gi = fmaf(a.weight_decay, p, gi);
+      if (a.momentum != 0.f) {
+        const float b = a.first_step ? gi : fmaf(a.momentum, m1[i], (1.f - a.dampening) * gi);
+        m1[i] = b;
+        gi = a.nesterov ? fmaf(a.momentum, b, gi) : b;
+      }
+      p = fmaf(-a.lr, gi, p);
+    } else {
+      if (a.kind == 1) gi = fmaf(a.weight_decay, p, gi);
+      else p *= (1.f - a.lr * a.weight_decay);
+      const float m = fmaf(a.beta1, m1[i], (1.f - a.beta1) * gi);
+      const float v = fmaf(a.beta2, m2[i], (1.f - a.beta2) * gi * gi);
+      m1[i] = m;
+      m2[i] = v;
+      const float denom = sqrtf(v) / sqrtf(a.bias_c2) + a.eps;
+      p = fmaf(-(a.lr / a.bias_c1), m / denom, p);
+    }
+    pw[i] = p;
+  }
+  if (a.kind != 0 || a.momentum != 0.f) {
+#pragma unroll
+    for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(s1 + k0 + i) = *reinterpret_cast<const float4*>(m1 + i);
+  }
+  if (a.kind != 0) {
+#pragma unroll
+    for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(s2 + k0 + i) = *reinterpret_cast<const float4*>(m2 + i);
+  }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
 fused_step_kernel(CollCtx g, PeerPtrs params, void* params_mc, float* __restrict__ s1, float* __restrict__ s2,
                   float* __restrict__ master, long long nvec, float scale, OptimArgs a) {
@@ -40,68 +86,70 @@ fused_step_kernel(CollCtx g, PeerPtrs params, void* params_mc, float* __restrict
   const long long lo = min(nvec, (long long)g.rank * per), hi = min(nvec, lo + per);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool mc_in = g.mc != nullptr, mc_out = params_mc != nullptr;
-  for (long long idx = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < hi; idx += stride) {
-    float gr[Tr::N];
+  constexpr int U = 2;   // vectors per thread per iteration: all gradient loads are issued before any math
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += U * stride) {
+    float gr[U][Tr::N];
+    bool valid[U];
     if (mc_in) {
-      const uint4 v = mc_ld_reduce_t<T>(static_cast<const uint4*>(g.mc) + idx);
-      vec_unpack<T>(v, gr);
-    } else {
-      uint4 v[kMaxPeers];
+      uint4 v[U];
 #pragma unroll
-      for (int p = 0; p < kMaxPeers; ++p)
-        if (p < world) v[p] = ld_peer_v4(static_cast<const uint4*>(g.data.p[p]) + idx);
-      float t[Tr::N];
-      vec_unpack<T>(v[0], gr);
-#pragma unroll
-      for (int p = 1; p < kMaxPeers; ++p)
-        if (p < world) {
-          vec_unpack<T>(v[p], t);
-#pragma unroll
-          for (int i = 0; i < Tr::N; ++i) gr[i] += t[i];
-        }
-    }
-    const long long k0 = (idx - lo) * Tr::N;
-    float pw[Tr::N];
-    if (master != nullptr) {
-#pragma unroll
-      for (int i = 0; i < Tr::N; ++i) pw[i] = master[k0 + i];
-    } else {
-      vec_unpack<T>(static_cast<const uint4*>(params.p[g.rank])[idx], pw);
-    }
-#pragma unroll
-    for (int i = 0; i < Tr::N; ++i) {
-      float gi = gr[i] * scale, p = pw[i];
-      if (a.kind == 0) {
-        gi = fmaf(a.weight_decay, p, gi);
-        if (a.momentum != 0.f) {
-          float b = a.first_step ? gi : fmaf(a.momentum, s1[k0 + i], (1.f - a.dampening) * gi);
-          s1[k0 + i] = b;
-          gi = a.nesterov ? fmaf(a.momentum, b, gi) : b;
-        }
-        p = fmaf(-a.lr, gi, p);
-      } else {
-        if (a.kind == 1) gi = fmaf(a.weight_decay, p, gi);
-        else p *= (1.f - a.lr * a.weight_decay);
-        const float m = fmaf(a.beta1, s1[k0 + i], (1.f - a.beta1) * gi);
-        const float v = fmaf(a.beta2, s2[k0 + i], (1.f - a.beta2) * gi * gi);
-        s1[k0 + i] = m;
-        s2[k0 + i] = v;
-        const float denom = sqrtf(v) / sqrtf(a.bias_c2) + a.eps;
-        p = fmaf(-(a.lr / a.bias_c1), m / denom, p);
+      for (int u = 0; u < U; ++u) {
+        valid[u] = i0 + u * stride < hi;
+        if (valid[u]) v[u] = mc_ld_reduce_t<T>(static_cast<const uint4*>(g.mc) + i0 + u * stride);
       }
-      pw[i] = p;
-    }
-    if (master != nullptr) {
 #pragma unroll
-      for (int i = 0; i < Tr::N; ++i) master[k0 + i] = pw[i];
-    }
-    const uint4 out = vec_pack<T>(pw);
-    if (mc_out) {
-      mc_st_v4(static_cast<uint4*>(params_mc) + idx, out);
+      for (int u = 0; u < U; ++u)
+        if (valid[u]) vec_unpack<T>(v[u], gr[u]);
     } else {
+      uint4 v[U][kMaxPeers];
 #pragma unroll
-      for (int p = 0; p < kMaxPeers; ++p)
-        if (p < world) st_peer_v4(static_cast<uint4*>(params.p[p]) + idx, out);
+      for (int u = 0; u < U; ++u) {
+        valid[u] = i0 + u * stride < hi;
+        if (valid[u]) {
+#pragma unroll
+          for (int p = 0; p < kMaxPeers; ++p)
+            if (p < world) v[u][p] = ld_peer_v4(static_cast<const uint4*>(g.data.p[p]) + i0 + u * stride);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+        float t[Tr::N];
+        vec_unpack<T>(v[u][0], gr[u]);
+#pragma unroll
+        for (int p = 1; p < kMaxPeers; ++p)
+          if (p < world) {
+            vec_unpack<T>(v[u][p], t);
+#pragma unroll
+            for (int i = 0; i < Tr::N; ++i) gr[u][i] += t[i];
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!valid[u]) continue;
+      const long long idx = i0 + u * stride;
+      const long long k0 = (idx - lo) * Tr::N;
+      float pw[Tr::N];
+      if (master != nullptr) {
+#pragma unroll
+        for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(pw + i) = *reinterpret_cast<const float4*>(master + k0 + i);
+      } else {
+        vec_unpack<T>(static_cast<const uint4*>(params.p[g.rank])[idx], pw);
+      }
+      optimizer_update<T>(gr[u], pw, s1, s2, k0, scale, a);
+      if (master != nullptr) {
+#pragma unroll
+        for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(master + k0 + i) = *reinterpret_cast<const float4*>(pw + i);
+      }
+      const uint4 out = vec_pack<T>(pw);
+      if (mc_out) {
+        mc_st_v4(static_cast<uint4*>(params_mc) + idx, out);
+      } else {
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+          if (p < world) st_peer_v4(static_cast<uint4*>(params.p[p]) + idx, out);
+      }
     }
   }
   coll_barrier(g, ep.base + 2);
@@ -131,9 +179,11 @@ int sdlc_fused_step(void* h, int channel, int grad_buf, int param_buf, long long
   a.bias_c1 = args[10]; a.bias_c2 = args[11];
   const size_t esz = dtype == kF32 ? 4 : 2;
   const long long nvec = (numel * (long long)esz + 15) / 16;
-  long long blocks = ((nvec + c->world - 1) / c->world + kThreads - 1) / kThreads;
+  long long blocks = ((nvec + c->world - 1) / c->world + kThreads * 2 - 1) / (kThreads * 2);
   if (blocks < 1) blocks = 1;
-  if (blocks > c->max_blocks) blocks = c->max_blocks;
+  // a single rank owns the whole bucket and only streams local HBM: give it more CTAs
+  const long long cap = c->world == 1 ? 96 : c->max_blocks;
+  if (blocks > cap) blocks = cap;
   if (dtype == kF32) {
     fused_step_kernel<float><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, a);
   } else if (dtype == kBF16) {

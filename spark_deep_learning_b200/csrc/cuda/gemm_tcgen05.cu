@@ -9,7 +9,7 @@
 //   warp 1   MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 x N x K16),
 //                           accumulators live in TMEM; tcgen05.commit frees smem slots / publishes tiles
 //   warp 2   TMEM allocator tcgen05.alloc of 2 x BLOCK_N fp32 columns (double-buffered accumulator)
-//   warps 4-7 epilogue      tcgen05.ld 32x32b.x32 -> +bias -> GELU -> bf16 -> 16-byte global stores,
+//   warps 4-11 epilogue     tcgen05.ld 32x32b.x32 -> +bias -> GELU -> bf16 -> swizzled smem -> 128-byte-row stores,
 //                           overlapped with the MMA of the next tile (tmem_full / tmem_empty barriers)
 //
 // Persistent: grid = min(#SMs, #tiles); every role walks the same static tile schedule.
@@ -128,7 +128,8 @@ struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 128;   // per epilogue warp: 32 rows x 64 bf16 columns
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 };
 
 // epilogue: 0 none, 1 GELU(tanh), 2 GELU(erf).  pre_act (optional) receives X.W^T + bias before the
@@ -144,7 +145,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr int kStages = L::kStages;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * L::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint8_t* staging = smem + kStages * L::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + L::kStagingBytes);
   uint64_t* full = bars;                    // [kStages]
   uint64_t* empty = bars + kStages;         // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages; // [2]
@@ -229,69 +231,81 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===== epilogue: TMEM -> registers -> bias / GELU -> bf16 -> global =====
+    // ===== epilogue: TMEM -> registers -> bias / GELU -> bf16 -> swizzled smem -> coalesced global stores =====
     const int q = (warp - kEpiWarp0) & 3;            // == warp % 4: TMEM lanes [32q, 32q+32)
     const int half = (warp - kEpiWarp0) >> 2;        // which half of the tile's columns this warp drains
     constexpr int kColsPerWarp = BLOCK_N / 2;
+    uint8_t* stage = staging + (warp - kEpiWarp0) * (32 * 128);
+    // thread = row while reading TMEM; 4 rows x 128 contiguous bytes per store instruction when writing out.
+    // 16-byte chunk j of row r lives at chunk (j ^ (r & 7)): conflict-free both ways.
+    auto stage_out = [&](const float* f, __nv_bfloat16* dst, int row0, int col) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 o;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+      }
+      __syncwarp();
+      const int chunk = lane & 7;
+      const int c = col + chunk * 8;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const uint4 o = *reinterpret_cast<const uint4*>(stage + r * 128 + ((chunk ^ (r & 7)) << 4));
+        if (row0 + r < M && c < N) *reinterpret_cast<uint4*>(dst + (size_t)(row0 + r) * N + c) = o;
+      }
+      __syncwarp();
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const int row0 = m_blk * BLOCK_M + q * 32;
 #pragma unroll 1
-      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
-        uint32_t v[32];
+      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 64) {
+        uint32_t v[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t* w = v + 32 * h;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]),
+                "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
+                "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+              : "r"(taddr + 32 * h));
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int col0 = n_blk * BLOCK_N + c0;
-        if (row < M) {
+        float f[64];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < N) {           // N % 8 == 0 is required by the host wrapper
-              float f[8];
+        for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(v[i]);
+        if (bias) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
-              if (bias) {                 // two 16-byte loads instead of eight scalar ones
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (pre_act) {
-                uint4 p;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                p.x = *reinterpret_cast<uint32_t*>(&h0); p.y = *reinterpret_cast<uint32_t*>(&h1);
-                p.z = *reinterpret_cast<uint32_t*>(&h2); p.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(pre_act + (size_t)row * N + col0 + j) = p;
-              }
-              if (epilogue == 1) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = gelu_tanh(f[i]);
-              } else if (epilogue == 2) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
-              }
-              uint4 o;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-              o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-              o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(out + (size_t)row * N + col0 + j) = o;
+          for (int j = 0; j < 64; j += 4) {
+            if (col0 + j < N) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
             }
           }
         }
+        if (pre_act) stage_out(f, pre_act, row0, col0);
+        if (epilogue == 1) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) f[i] = gelu_tanh(f[i]);
+        } else if (epilogue == 2) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) f[i] = gelu_erf(f[i]);
+        }
+        stage_out(f, out, row0, col0);
       }
       tc_fence_before();
       __syncwarp();

@@ -43,7 +43,7 @@ class Config(object):
         self.shm_stage_bytes = _env(["SPARKDL_SHM_STAGE_BYTES"], 8 << 20, int)
         # --- GPU collectives ---------------------------------------------------------------
         # message size (bytes) at or below which the one-shot kernel is used
-        self.oneshot_max_bytes = _env(["SPARKDL_ONESHOT_MAX_BYTES"], 512 << 10, int)
+        self.oneshot_max_bytes = _env(["SPARKDL_ONESHOT_MAX_BYTES"], 16 << 10, int)   # measured crossover, profiles/
         # use NVLS multicast (multimem.*) when the hardware offers it
         self.use_multicast = _env(["SPARKDL_USE_MULTICAST"], True, _bool)
         # symmetric-memory transport: auto | vmm | ipc
