@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--no-fused-optimizer", action="store_true")
     ap.add_argument("--no-fused-model", action="store_true")
     ap.add_argument("--wire", default=None, choices=[None, "bf16", "fp16", "fp8"])
+    ap.add_argument("--no-cuda-graph", action="store_true")
     return ap.parse_args()
 
 
@@ -69,7 +70,7 @@ def main():
         cloudpickle.register_pickle_by_value(sparkdl_main)   # workers need not import benchmarks/
         fn = sparkdl_main.train
         kwargs = {"fused_optimizer": not args.no_fused_optimizer, "fused_model": not args.no_fused_model,
-                  "wire": args.wire}
+                  "wire": args.wire, "cuda_graph": not args.no_cuda_graph}
         if world > 1:
             os.environ["SPARKDL_EXTERNAL_GANG"] = "1"
 
@@ -115,7 +116,7 @@ def main():
         "loss": res.get("loss"),
     }
     if args.impl == "ours":
-        out["runtime"] = {k: res.get(k) for k in ("transport", "multicast", "buckets")}
+        out["runtime"] = {k: res.get(k) for k in ("transport", "multicast", "buckets", "cuda_graph")}
     else:
         out["reference_note"] = ("unmodified sparkdl 2.2.0-db1 HorovodRunner (in-process run); gradient exchange = "
                                  "torch DDP over NCCL 2.28.9, the NCCL-via-torch stand-in for horovod+NCCL")

@@ -64,10 +64,10 @@ def fused_step():
     g, p = vg.alloc(n * 4)[0], vg.alloc(n * 4)[0]
     ns = lib.sdlc_fused_state_elems(c._h, n, 6)
     s1, s2 = torch.zeros(ns, device="cuda"), torch.zeros(ns, device="cuda")
-    args = (ctypes.c_float * 16)(*([2, 1e-3, 0.01, 0, 0, 0, 0, 0.9, 0.999, 1e-8, 0.1, 0.001] + [0.0] * 4))
+    hyper = torch.tensor([2, 1e-3, 0.01, 0, 0, 0, 0.9, 0.999, 1e-8, 5.0] + [0.0] * 6, device="cuda")
     s = vg.streams[0].cuda_stream
     for _ in range(5):
-        lib.sdlc_fused_step(c._h, 1, g.id, p.id, n, 6, ctypes.c_void_p(s1.data_ptr()), ctypes.c_void_p(s2.data_ptr()), None, 1.0, args, s)
+        lib.sdlc_fused_step(c._h, 1, g.id, p.id, n, 6, ctypes.c_void_p(s1.data_ptr()), ctypes.c_void_p(s2.data_ptr()), None, 1.0, ctypes.c_void_p(hyper.data_ptr()), s)
     torch.cuda.synchronize()
 
 

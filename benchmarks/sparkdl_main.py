@@ -6,7 +6,7 @@ model zoo.  Gradient averaging + optimizer update run in the fused sm_100a peer-
 
 
 def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, seq_len=128,
-          fused_optimizer=True, fused_model=True, wire=None):
+          fused_optimizer=True, fused_model=True, wire=None, cuda_graph=True):
     import os
     import time
 
@@ -58,6 +58,18 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
         hvd.barrier()
         torch.cuda.synchronize()
 
+    graphed = False
+    if cuda_graph and fused_optimizer:
+        # the whole step (incl. the peer-memory optimizer kernels) replays as one CUDA graph
+        from spark_deep_learning_b200.utils.graph import GraphedTrainStep
+        eager_step = step
+        try:
+            step = GraphedTrainStep(eager_step, (dx, dy), warmup=3)
+            graphed = True
+        except Exception as e:  # pylint: disable=broad-except
+            print("CUDA graph capture failed, running eagerly: %r" % (e,), flush=True)
+            torch.cuda.synchronize()
+            step = eager_step
     for _ in range(warmup):
         step(dx, dy)
     barrier()
@@ -71,6 +83,8 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = launch_counter.total(comm) - l0
+    if graphed:
+        launches = step.launches_per_replay * steps
 
     # end to end through the public input pipeline: every step copies its inputs from pinned host
     # memory (prefetched one step ahead on a copy stream) and reads its loss back on the host
@@ -101,6 +115,6 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
            "d2h_bytes": 4, "e2e_wall_ms": e2e_wall_ms, "loss": loss_val, "world": world, "batch": batch,
            "gpu_launches": int(launches),
            "transport": getattr(comm, "transport", None), "multicast": getattr(comm, "multicast", None),
-           "buckets": len(opt.bucket_summary())}
+           "buckets": len(opt.bucket_summary()), "cuda_graph": graphed}
     hvd.shutdown()
     return res

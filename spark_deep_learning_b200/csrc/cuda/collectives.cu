@@ -165,28 +165,30 @@ allreduce_multimem_kernel(CollCtx c, long long nvec, float scale) {
 // 16-bit cast or block-scaled fp8 (e4m3 payload + one fp32 scale per 128 elements), accumulated in
 // fp32.  Quantise -> barrier -> reduce slice + requantise + push -> barrier -> dequantise: one kernel.
 // =====================================================================================================
-constexpr int kUnit = 128;  // elements per scale block; one warp handles one unit, 4 elements per lane
+constexpr int kUnit = 128;  // elements per scale block; one HALF-warp handles one unit, 8 elements per lane
 
-template <typename S> __device__ __forceinline__ void load4(const S* p, float* f);
-template <> __device__ __forceinline__ void load4<float>(const float* p, float* f) {
-  const float4 v = *reinterpret_cast<const float4*>(p);
-  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+template <typename S> __device__ __forceinline__ void load8(const S* p, float* f);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float* f) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
-template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
-  const uint2 v = *reinterpret_cast<const uint2*>(p);
-  bf16x2_to_f(v.x, f[0], f[1]); bf16x2_to_f(v.y, f[2], f[3]);
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  bf16x2_to_f(v.x, f[0], f[1]); bf16x2_to_f(v.y, f[2], f[3]); bf16x2_to_f(v.z, f[4], f[5]); bf16x2_to_f(v.w, f[6], f[7]);
 }
-template <typename S> __device__ __forceinline__ void store4(S* p, const float* f);
-template <> __device__ __forceinline__ void store4<float>(float* p, const float* f) {
-  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+template <typename S> __device__ __forceinline__ void store8(S* p, const float* f);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
-template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
-  *reinterpret_cast<uint2*>(p) = make_uint2(f_to_bf16x2(f[0], f[1]), f_to_bf16x2(f[2], f[3]));
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(f_to_bf16x2(f[0], f[1]), f_to_bf16x2(f[2], f[3]), f_to_bf16x2(f[4], f[5]), f_to_bf16x2(f[6], f[7]));
 }
 
-__device__ __forceinline__ float warp_max(float v) {
+// max over the 16 lanes of a half-warp (xor offsets < 16 never cross the half)
+__device__ __forceinline__ float halfwarp_max(float v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 
@@ -203,41 +205,60 @@ __device__ __forceinline__ void dequant_fp8x4(uint32_t q, float s, float* f) {
   f[0] = fa.x * s; f[1] = fa.y * s; f[2] = fb.x * s; f[3] = fb.y * s;
 }
 
-// wire layouts: 16-bit: unit u at byte u*256, lane l at +8l.  fp8: payload unit u at byte u*128 (+4l),
-// scales at byte n_units*128 + 4u.
+// wire layouts (hl = lane within the half-warp, 8 elements each):
+//   16-bit: unit u at byte u*256, lane at +16*hl.   fp8: payload unit u at byte u*128 (+8*hl), scales at
+//   byte n_units*128 + 4u (one fp32 per 128-element block).
+struct WireRaw { uint4 q; float s; };
+
 template <int WIRE>
-__device__ __forceinline__ void wire_store(char* base, long long n_units, long long u, int lane, const float* f, bool remote) {
+__device__ __forceinline__ void wire_store(char* base, long long n_units, long long u, int hl, const float* f, bool remote) {
   if (WIRE == kWireFP8) {
-    float amax = fmaxf(fmaxf(fabsf(f[0]), fabsf(f[1])), fmaxf(fabsf(f[2]), fabsf(f[3])));
-    amax = warp_max(amax);
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(f[i]));
+    amax = halfwarp_max(amax);
     const float s = amax > 0.f ? amax * (1.0f / 448.0f) : 1.0f;
-    const uint32_t q = quant_fp8x4(f, 1.0f / s);
+    const float inv = 1.0f / s;
+    const uint2 q = make_uint2(quant_fp8x4(f, inv), quant_fp8x4(f + 4, inv));
     if (remote) {
-      st_peer_u32(base + u * kUnit + lane * 4, q);
-      if (lane == 0) st_peer_u32(base + n_units * kUnit + u * 4, __float_as_uint(s));
+      st_peer_v2(base + u * kUnit + hl * 8, q);
+      if (hl == 0) st_peer_u32(base + n_units * kUnit + u * 4, __float_as_uint(s));
     } else {
-      *reinterpret_cast<uint32_t*>(base + u * kUnit + lane * 4) = q;
-      if (lane == 0) *reinterpret_cast<float*>(base + n_units * kUnit + u * 4) = s;
+      *reinterpret_cast<uint2*>(base + u * kUnit + hl * 8) = q;
+      if (hl == 0) *reinterpret_cast<float*>(base + n_units * kUnit + u * 4) = s;
     }
   } else {
-    uint2 q;
-    if (WIRE == kWireBF16) q = make_uint2(f_to_bf16x2(f[0], f[1]), f_to_bf16x2(f[2], f[3]));
-    else q = make_uint2(f_to_f16x2(f[0], f[1]), f_to_f16x2(f[2], f[3]));
-    if (remote) st_peer_v2(base + u * (kUnit * 2) + lane * 8, q);
-    else *reinterpret_cast<uint2*>(base + u * (kUnit * 2) + lane * 8) = q;
+    uint4 q;
+    if (WIRE == kWireBF16) q = make_uint4(f_to_bf16x2(f[0], f[1]), f_to_bf16x2(f[2], f[3]), f_to_bf16x2(f[4], f[5]), f_to_bf16x2(f[6], f[7]));
+    else q = make_uint4(f_to_f16x2(f[0], f[1]), f_to_f16x2(f[2], f[3]), f_to_f16x2(f[4], f[5]), f_to_f16x2(f[6], f[7]));
+    if (remote) st_peer_v4(base + u * (kUnit * 2) + hl * 16, q);
+    else *reinterpret_cast<uint4*>(base + u * (kUnit * 2) + hl * 16) = q;
   }
 }
 
+// issue the loads of one unit (raw bits); decode later so that the loads of all peers are in flight together
 template <int WIRE>
-__device__ __forceinline__ void wire_load(const char* base, long long n_units, long long u, int lane, float* f) {
+__device__ __forceinline__ WireRaw wire_load_raw(const char* base, long long n_units, long long u, int hl) {
+  WireRaw r;
   if (WIRE == kWireFP8) {
-    const uint32_t q = ld_peer_u32(base + u * kUnit + lane * 4);
-    const float s = __uint_as_float(ld_peer_u32(base + n_units * kUnit + u * 4));
-    dequant_fp8x4(q, s, f);
+    const uint2 q = ld_peer_v2(base + u * kUnit + hl * 8);
+    r.q = make_uint4(q.x, q.y, 0u, 0u);
+    r.s = __uint_as_float(ld_peer_u32(base + n_units * kUnit + u * 4));
   } else {
-    const uint2 q = ld_peer_v2(base + u * (kUnit * 2) + lane * 8);
-    if (WIRE == kWireBF16) { bf16x2_to_f(q.x, f[0], f[1]); bf16x2_to_f(q.y, f[2], f[3]); }
-    else { f16x2_to_f(q.x, f[0], f[1]); f16x2_to_f(q.y, f[2], f[3]); }
+    r.q = ld_peer_v4(base + u * (kUnit * 2) + hl * 16);
+    r.s = 1.f;
+  }
+  return r;
+}
+template <int WIRE>
+__device__ __forceinline__ void wire_decode(const WireRaw& r, float* f) {
+  if (WIRE == kWireFP8) {
+    dequant_fp8x4(r.q.x, r.s, f);
+    dequant_fp8x4(r.q.y, r.s, f + 4);
+  } else if (WIRE == kWireBF16) {
+    bf16x2_to_f(r.q.x, f[0], f[1]); bf16x2_to_f(r.q.y, f[2], f[3]); bf16x2_to_f(r.q.z, f[4], f[5]); bf16x2_to_f(r.q.w, f[6], f[7]);
+  } else {
+    f16x2_to_f(r.q.x, f[0], f[1]); f16x2_to_f(r.q.y, f[2], f[3]); f16x2_to_f(r.q.z, f[4], f[5]); f16x2_to_f(r.q.w, f[6], f[7]);
   }
 }
 
@@ -245,57 +266,62 @@ template <typename S, int WIRE>
 __global__ void __launch_bounds__(kThreads)
 allreduce_wire_kernel(CollCtx c, S* storage, long long n, float pre, float post) {
   EpochScope ep(c);
-  const int world = c.world, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int world = c.world, hl = threadIdx.x & 15, hw = threadIdx.x >> 4, hpb = blockDim.x >> 4;
   const long long n_units = ceil_div_ll(n, kUnit);
   const long long upr = ceil_div_ll(n_units, world);
   char* my_wire = static_cast<char*>(c.data.p[c.rank]);
+  const long long step = (long long)gridDim.x * hpb;
   // phase 0: quantise my gradients into my wire buffer.  Block b owns the units j (within every
   // slice) with j % gridDim.x == b - exactly the units block b of the slice owner will read.
   for (int s = 0; s < world; ++s) {
     const long long s_lo = min(n_units, (long long)s * upr), s_len = min(n_units, s_lo + upr) - s_lo;
-    for (long long j = blockIdx.x + (long long)gridDim.x * warp; j < s_len; j += (long long)gridDim.x * wpb) {
-      const long long u = s_lo + j, e = u * kUnit + lane * 4;
-      float f[4] = {0.f, 0.f, 0.f, 0.f};
-      if (e < n) {
-        load4<S>(storage + e, f);
+    for (long long j = blockIdx.x + (long long)gridDim.x * hw; j < s_len; j += step) {
+      const long long u = s_lo + j, e = u * kUnit + hl * 8;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (e < n) {                                  // n % 8 == 0 (checked on the host)
+        load8<S>(storage + e, f);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) f[i] *= pre;
+        for (int i = 0; i < 8; ++i) f[i] *= pre;
       }
-      wire_store<WIRE>(my_wire, n_units, u, lane, f, false);
+      wire_store<WIRE>(my_wire, n_units, u, hl, f, false);
     }
   }
   coll_barrier(c, ep.base + 1);
   // phase 1: reduce my slice over all peers (fp32), requantise, push to every peer's wire buffer
   {
     const long long s_lo = min(n_units, (long long)c.rank * upr), s_len = min(n_units, s_lo + upr) - s_lo;
-    for (long long j = blockIdx.x + (long long)gridDim.x * warp; j < s_len; j += (long long)gridDim.x * wpb) {
+    for (long long j = blockIdx.x + (long long)gridDim.x * hw; j < s_len; j += step) {
       const long long u = s_lo + j;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      WireRaw raw[kMaxPeers];
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < world) raw[p] = wire_load_raw<WIRE>(static_cast<const char*>(c.data.p[p]), n_units, u, hl);
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int p = 0; p < kMaxPeers; ++p) {
         if (p < world) {
-          float f[4];
-          wire_load<WIRE>(static_cast<const char*>(c.data.p[p]), n_units, u, lane, f);
+          float f[8];
+          wire_decode<WIRE>(raw[p], f);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] += f[i];
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] *= post;
+      for (int i = 0; i < 8; ++i) acc[i] *= post;
 #pragma unroll
       for (int p = 0; p < kMaxPeers; ++p)
-        if (p < world) wire_store<WIRE>(static_cast<char*>(c.data.p[p]), n_units, u, lane, acc, true);
+        if (p < world) wire_store<WIRE>(static_cast<char*>(c.data.p[p]), n_units, u, hl, acc, true);
     }
   }
   coll_barrier(c, ep.base + 2);
   // phase 2: dequantise the reduced wire buffer back into my storage
   for (int s = 0; s < world; ++s) {
     const long long s_lo = min(n_units, (long long)s * upr), s_len = min(n_units, s_lo + upr) - s_lo;
-    for (long long j = blockIdx.x + (long long)gridDim.x * warp; j < s_len; j += (long long)gridDim.x * wpb) {
-      const long long u = s_lo + j, e = u * kUnit + lane * 4;
-      float f[4];
-      wire_load<WIRE>(my_wire, n_units, u, lane, f);
-      if (e < n) store4<S>(storage + e, f);
+    for (long long j = blockIdx.x + (long long)gridDim.x * hw; j < s_len; j += step) {
+      const long long u = s_lo + j, e = u * kUnit + hl * 8;
+      float f[8];
+      wire_decode<WIRE>(wire_load_raw<WIRE>(my_wire, n_units, u, hl), f);
+      if (e < n) store8<S>(storage + e, f);
     }
   }
   ep.commit(c, 2);
@@ -572,8 +598,15 @@ int sdlc_allreduce_wire(void* h, int channel, void* storage, long long numel, in
   Comm* c = static_cast<Comm*>(h);
   cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
   const CollCtx ctx = c->make_ctx(channel, wire_buf, (size_t)wire_off);
+  if ((numel & 7) != 0) {
+    c->last_error = "wire-format allreduce needs a multiple of 8 elements";
+    return -1;
+  }
   const long long units = ceil_div_ll(numel, kUnit);
-  const int blocks = pick_blocks(c, ceil_div_ll(units, c->world), kThreads / 32 * 4);
+  // phases 0 and 2 are local HBM passes over the whole tensor: use up to kMaxBlocks CTAs, not just comm_ctas
+  long long want = ceil_div_ll(units / (c->world > 0 ? 1 : 1), (kThreads / 16) * 4);
+  if (want < 1) want = 1;
+  const int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : want);
   if (dtype == kF32) {
     float* p = static_cast<float*>(storage);
     if (wire == kWireBF16) allreduce_wire_kernel<float, kWireBF16><<<blocks, kThreads, 0, s>>>(ctx, p, numel, pre, post);

@@ -23,6 +23,23 @@ struct OptimArgs {
   float beta1, beta2, eps, bias_c1, bias_c2;  // bias_c = 1 - beta^t
 };
 
+// Hyper-parameters live in DEVICE memory (16 floats per param group) so that a captured CUDA graph of the
+// training step keeps working when the learning rate or the step count changes:
+//   [0] kind  [1] lr  [2] weight_decay  [3] momentum  [4] dampening  [5] nesterov  [6] beta1  [7] beta2
+//   [8] eps   [9] number of optimizer steps already taken (advanced on the device by step_advance_kernel)
+__device__ __forceinline__ OptimArgs load_hyper(const float* __restrict__ h) {
+  OptimArgs a;
+  a.kind = (int)h[0]; a.lr = h[1]; a.weight_decay = h[2]; a.momentum = h[3]; a.dampening = h[4];
+  a.nesterov = (int)h[5]; a.beta1 = h[6]; a.beta2 = h[7]; a.eps = h[8];
+  const float t = h[9] + 1.f;
+  a.first_step = h[9] == 0.f;
+  a.bias_c1 = 1.f - powf(a.beta1, t);
+  a.bias_c2 = 1.f - powf(a.beta2, t);
+  return a;
+}
+
+__global__ void step_advance_kernel(float* hyper) { hyper[9] += 1.f; }
+
 template <typename T> __device__ __forceinline__ uint4 mc_ld_reduce_t(const void* p);
 template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<float>(const void* p) { return mc_ld_reduce_f32(p); }
 template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<__nv_bfloat16>(const void* p) { return mc_ld_reduce_bf16(p); }
@@ -77,8 +94,9 @@ __device__ __forceinline__ void optimizer_update(float* gr, float* pw, float* __
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 fused_step_kernel(CollCtx g, PeerPtrs params, void* params_mc, float* __restrict__ s1, float* __restrict__ s2,
-                  float* __restrict__ master, long long nvec, float scale, OptimArgs a) {
+                  float* __restrict__ master, long long nvec, float scale, const float* __restrict__ hyper) {
   using Tr = VecTraits<T>;
+  const OptimArgs a = load_hyper(hyper);
   EpochScope ep(g);
   coll_barrier(g, ep.base + 1);
   const int world = g.world;
@@ -162,9 +180,9 @@ using namespace sdlc;
 
 extern "C" {
 
-// args: float[16] = {kind, lr, wd, momentum, dampening, nesterov, first_step, beta1, beta2, eps, bias_c1, bias_c2}
+// hyper: DEVICE pointer to the 16-float hyper-parameter block of the bucket's param group (see load_hyper)
 int sdlc_fused_step(void* h, int channel, int grad_buf, int param_buf, long long numel, int dtype, float* s1, float* s2,
-                    float* master, float scale, const float* args, unsigned long long stream) {
+                    float* master, float scale, const float* hyper, unsigned long long stream) {
   Comm* c = static_cast<Comm*>(h);
   cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
   CollCtx g = c->make_ctx(channel, grad_buf, 0);
@@ -173,10 +191,6 @@ int sdlc_fused_step(void* h, int channel, int grad_buf, int param_buf, long long
   memset(&pp, 0, sizeof(pp));
   for (int r = 0; r < c->world; ++r) pp.p[r] = pb.ptrs[r];
   void* pmc = (pb.mc && c->use_mc) ? pb.mc : nullptr;
-  OptimArgs a;
-  a.kind = (int)args[0]; a.lr = args[1]; a.weight_decay = args[2]; a.momentum = args[3]; a.dampening = args[4];
-  a.nesterov = (int)args[5]; a.first_step = (int)args[6]; a.beta1 = args[7]; a.beta2 = args[8]; a.eps = args[9];
-  a.bias_c1 = args[10]; a.bias_c2 = args[11];
   const size_t esz = dtype == kF32 ? 4 : 2;
   const long long nvec = (numel * (long long)esz + 15) / 16;
   long long blocks = ((nvec + c->world - 1) / c->world + kThreads * 2 - 1) / (kThreads * 2);
@@ -185,11 +199,11 @@ int sdlc_fused_step(void* h, int channel, int grad_buf, int param_buf, long long
   const long long cap = c->world == 1 ? 96 : c->max_blocks;
   if (blocks > cap) blocks = cap;
   if (dtype == kF32) {
-    fused_step_kernel<float><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, a);
+    fused_step_kernel<float><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, hyper);
   } else if (dtype == kBF16) {
-    fused_step_kernel<__nv_bfloat16><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, a);
+    fused_step_kernel<__nv_bfloat16><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, hyper);
   } else if (dtype == kF16) {
-    fused_step_kernel<__half><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, a);
+    fused_step_kernel<__half><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, hyper);
   } else {
     c->last_error = "fused optimizer step supports fp32 / bf16 / fp16 parameters";
     return -1;
@@ -201,6 +215,15 @@ int sdlc_fused_step(void* h, int channel, int grad_buf, int param_buf, long long
   }
   c->launches++;
   return 0;
+}
+
+// advance the device-side step counter of one param group (launched once per optimizer step, after its buckets)
+int sdlc_step_advance(void* h, int channel, float* hyper, unsigned long long stream) {
+  Comm* c = static_cast<Comm*>(h);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->streams[channel];
+  step_advance_kernel<<<1, 1, 0, s>>>(hyper);
+  c->launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // elements of optimizer state this rank must allocate for a bucket of `numel` elements

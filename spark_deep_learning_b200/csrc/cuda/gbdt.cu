@@ -39,11 +39,13 @@ gbdt_hist_kernel(const uint8_t* __restrict__ bins, const int2* __restrict__ gh, 
 }
 
 // K8 fused: local build -> device-local grid barrier -> cross-rank two-shot int64 reduction.
-__global__ void __launch_bounds__(kThreads)
+// The build phase wants the whole GPU (one 1024-thread CTA per SM, all co-resident for the local barrier);
+// the cross-rank phase is run by the first `cross_blocks` CTAs only (flag slots exist for kMaxBlocks CTAs).
+constexpr int kHistThreads = 1024;
+__global__ void __launch_bounds__(kHistThreads, 2)
 gbdt_hist_allreduce_kernel(CollCtx c, const uint8_t* __restrict__ bins, const int2* __restrict__ gh,
                            const int* __restrict__ pos, long long n, int F, long long hist_elems,
-                           unsigned int* grid_ctr, unsigned int grid_epoch) {
-  EpochScope ep(c);
+                           unsigned int* grid_ctr, unsigned int grid_epoch, int cross_blocks) {
   unsigned long long* hist = static_cast<unsigned long long*>(c.data.p[c.rank]);
   hist_accumulate(bins, gh, pos, hist, n, F, (long long)blockIdx.x * blockDim.x + threadIdx.x,
                   (long long)gridDim.x * blockDim.x);
@@ -63,12 +65,14 @@ gbdt_hist_allreduce_kernel(CollCtx c, const uint8_t* __restrict__ bins, const in
     __threadfence();
   }
   __syncthreads();
+  if ((int)blockIdx.x >= cross_blocks) return;
+  EpochScope ep(c);
   coll_barrier(c, ep.base + 1);
   const long long nvec = (hist_elems + 1) / 2;  // 2 int64 per 16-byte vector
   const int world = c.world;
   const long long per = (nvec + world - 1) / world;
   const long long lo = min(nvec, (long long)c.rank * per), hi = min(nvec, lo + per);
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long stride = (long long)cross_blocks * blockDim.x;
   for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
     long long a0 = 0, a1 = 0;
 #pragma unroll
@@ -139,12 +143,14 @@ int sdlc_gbdt_hist_allreduce(void* h, int channel, int buf, const void* bins, co
   // memset before it and the reads after it
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const CollCtx ctx = c->make_ctx(channel, buf, 0);
-  // every CTA must be co-resident (device-local barrier): at most one CTA per SM, bounded by kMaxBlocks
-  int blocks = c->max_blocks * 4;
-  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
-  gbdt_hist_allreduce_kernel<<<blocks, kThreads, 0, s>>>(ctx, static_cast<const uint8_t*>(bins), static_cast<const int2*>(gh),
-                                                         static_cast<const int*>(pos), n, F, hist_elems,
-                                                         static_cast<unsigned int*>(grid_ctr), grid_epoch);
+  // every CTA must be co-resident (device-local barrier): two 1024-thread CTAs per SM (32 registers/thread)
+  int blocks = 0;
+  cudaDeviceGetAttribute(&blocks, cudaDevAttrMultiProcessorCount, c->device);
+  blocks = blocks < 1 ? 1 : 2 * blocks;
+  const int cross = blocks < kMaxBlocks ? blocks : kMaxBlocks;
+  gbdt_hist_allreduce_kernel<<<blocks, kHistThreads, 0, s>>>(ctx, static_cast<const uint8_t*>(bins), static_cast<const int2*>(gh),
+                                                             static_cast<const int*>(pos), n, F, hist_elems,
+                                                             static_cast<unsigned int*>(grid_ctr), grid_epoch, cross);
   if (cudaGetLastError() != cudaSuccess) {
     c->last_error = "gbdt_hist_allreduce launch failed";
     return -1;

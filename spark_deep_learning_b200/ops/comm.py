@@ -89,7 +89,8 @@ def load():
         "sdlc_reducescatter": (i32, [vp, i32, i32, vp, i64, i64, i32, i32, f32, f32, i64, u64]),
         "sdlc_pack": (i32, [vp, i32, P(u64), P(i64), P(i64), i32, i32, u64]),
         "sdlc_scale": (i32, [vp, vp, i64, i32, f32, u64]),
-        "sdlc_fused_step": (i32, [vp, i32, i32, i32, i64, i32, vp, vp, vp, f32, P(f32), u64]),
+        "sdlc_fused_step": (i32, [vp, i32, i32, i32, i64, i32, vp, vp, vp, f32, vp, u64]),
+        "sdlc_step_advance": (i32, [vp, i32, vp, u64]),
         "sdlc_fused_state_elems": (i64, [vp, i64, i32]),
         "sdlc_fused_slice_start": (i64, [vp, i64, i32]),
     }
@@ -403,18 +404,38 @@ class SymmComm(object):
     # ---------------------------------------------------------------------------------------------
     # fused reduce-scatter + optimizer + all-gather (DistributedOptimizer(fused=True))
     # ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def hyper_values(opt, group):
+        """The 9 static entries of a param group's device hyper-parameter block (see fused_optim.cu)."""
+        if isinstance(opt, torch.optim.SGD):
+            return [0, group["lr"], group["weight_decay"], group["momentum"], group["dampening"],
+                    1.0 if group["nesterov"] else 0.0, 0.0, 0.0, 0.0]
+        b1, b2 = group["betas"]
+        kind = 2 if isinstance(opt, torch.optim.AdamW) else 1
+        return [kind, group["lr"], group["weight_decay"], 0.0, 0.0, 0.0, b1, b2, group["eps"]]
+
     def fused_optimizer_step(self, opt, b, pre, post):
+        """Launch the fused reduce-scatter + optimizer + all-gather kernel for bucket ``b``."""
         lib = self._lib
         s = self.channel_stream(1)
-        lib.sdlc_stream_wait_event(s, self.record_ready_event())
         code = _TORCH_DTYPE[b.dtype]
         st = b.state
-        group = opt._group_of_bucket(b)
+        gi = opt._bucket_group[b.index]
+        group = opt.param_groups[gi]
+        dev = torch.device("cuda", self.device)
+        hyper = opt._hyper.get(gi)
+        if hyper is None:
+            vals = [float(v) for v in self.hyper_values(opt, group)] + [0.0] * 7
+            hyper = {"dev": torch.tensor(vals, dtype=torch.float32, device=dev), "lr": float(group["lr"]),
+                     "advanced": False}
+            opt._hyper[gi] = hyper
+        elif float(group["lr"]) != hyper["lr"]:
+            # lr schedulers: refresh the device copy on the producer stream, ordered before the kernel
+            hyper["dev"][1].fill_(float(group["lr"]))
+            hyper["lr"] = float(group["lr"])
         if st is None:
             n = lib.sdlc_fused_state_elems(self._h, b.numel, code)
-            dev = torch.device("cuda", self.device)
-            st = {"s1": torch.zeros(n, dtype=torch.float32, device=dev), "step": 0,
-                  "s2": None, "master": None}
+            st = {"s1": torch.zeros(n, dtype=torch.float32, device=dev), "s2": None, "master": None}
             if not isinstance(opt, torch.optim.SGD):
                 st["s2"] = torch.zeros(n, dtype=torch.float32, device=dev)
             if b.dtype != torch.float32:
@@ -425,25 +446,30 @@ class SymmComm(object):
                 st["master"] = m
             b.state = st
             torch.cuda.current_stream(self.device).synchronize()
-        st["step"] += 1
-        t = st["step"]
-        if isinstance(opt, torch.optim.SGD):
-            args = [0, group["lr"], group["weight_decay"], group["momentum"], group["dampening"],
-                    1.0 if group["nesterov"] else 0.0, 1.0 if t == 1 else 0.0, 0, 0, 0, 1, 1]
-        else:
-            b1, b2 = group["betas"]
-            kind = 2 if isinstance(opt, torch.optim.AdamW) else 1
-            args = [kind, group["lr"], group["weight_decay"], 0, 0, 0, 0, b1, b2, group["eps"],
-                    1.0 - b1 ** t, 1.0 - b2 ** t]
-        arr = (ctypes.c_float * 16)(*([float(a) for a in args] + [0.0] * (16 - len(args))))
+        lib.sdlc_stream_wait_event(s, self.record_ready_event())
         rc = lib.sdlc_fused_step(
             self._h, 1, b.sym.id, b.psym.id, b.numel, code, ctypes.c_void_p(st["s1"].data_ptr()),
             ctypes.c_void_p(st["s2"].data_ptr() if st["s2"] is not None else 0),
             ctypes.c_void_p(st["master"].data_ptr() if st["master"] is not None else 0),
-            float(pre * post), arr, s)
+            float(pre * post), ctypes.c_void_p(hyper["dev"].data_ptr()), s)
         if rc:
             raise CommError("fused optimizer step failed: %s" % self._err())
+        hyper["advanced"] = False
         return lib.sdlc_record_event(self._h, s)
+
+    def fused_step_advance(self, opt):
+        """After the last bucket of an optimizer step: bump every group's device-side step counter (on the
+        channel stream, behind the bucket kernels) and return an event the caller's stream must wait on."""
+        lib = self._lib
+        s = self.channel_stream(1)
+        did = False
+        for hyper in opt._hyper.values():
+            if not hyper["advanced"]:
+                if lib.sdlc_step_advance(self._h, 1, ctypes.c_void_p(hyper["dev"].data_ptr()), s):
+                    raise CommError("step_advance failed")
+                hyper["advanced"] = True
+                did = True
+        return lib.sdlc_record_event(self._h, s) if did else 0
 
     # ---------------------------------------------------------------------------------------------
     def close(self):

@@ -88,6 +88,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self._next_launch = 0
         self._hooks = []
         self._fused = bool(fused) and hvd.is_initialized()
+        self._hyper = {}          # param-group index -> device hyper-parameter block (fused path)
         self._step_count = 0
         if hvd.is_initialized():
             self._build_buckets([p for _, p in named_parameters if id(p) in all_ids])
@@ -251,7 +252,20 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             if b.done_event:
                 comm.current_stream_wait(b.done_event)
                 b.done_event = 0
+        if self._fused and comm is not None:
+            ev = comm.fused_step_advance(self)
+            if ev:
+                comm.current_stream_wait(ev)      # also re-joins the channel stream under graph capture
         self._synchronized = True
+
+    def sync_hyperparams(self):
+        """Push the current ``lr`` of every param group to the device (call before replaying a captured
+        step after a scheduler changed it; the eager path does this automatically)."""
+        for gi, hyper in self._hyper.items():
+            lr = float(self.param_groups[gi]["lr"])
+            if lr != hyper["lr"]:
+                hyper["dev"][1].fill_(lr)
+                hyper["lr"] = lr
 
     @contextlib.contextmanager
     def skip_synchronize(self):

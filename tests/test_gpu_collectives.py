@@ -105,7 +105,7 @@ def test_repeated_launches_reuse_flags(lib):
 def test_allreduce_wire_formats(lib, wire, tol, world):
     """K6/K7: fp32 storage, 16-bit or block-scaled-fp8 payload on the wire, fp32 accumulation."""
     from spark_deep_learning_b200.ops.comm import WIRE
-    n = 128 * 37 + 44           # not a multiple of the 128-element scale block
+    n = 128 * 37 + 40           # not a multiple of the 128-element scale block (but of 8: one 16-byte lane)
     vg = _group(world)
     grads = [torch.empty(n, device="cuda") for _ in range(world)]
     g = torch.Generator().manual_seed(5)
@@ -215,19 +215,20 @@ def test_fused_optimizer_step_matches_torch(lib, kind, dtype):
         k = max(0, min(ns, n - lo))
         m[:k] = p0[lo:lo + k].cuda()
         master.append(m)
+    if kind.startswith("sgd"):
+        hv = [0, 0.1, 0.01, 0.9, 0.0, 1.0 if kind.endswith("nesterov") else 0.0, 0, 0, 0]
+    else:
+        hv = [1 if kind == "adam" else 2, 0.01, 0.01 if kind == "adam" else 0.1, 0, 0, 0, 0.9, 0.999, 1e-8]
+    hyper = [torch.tensor([float(v) for v in hv] + [0.0] * 7, device="cuda") for _ in range(world)]
     for t in range(1, steps + 1):
         grads = _fill(gb, dtype, n, seed=100 + t)
         ref_p.grad = (sum(g.float() for g in grads) / world)
         ropt.step()
-        if kind.startswith("sgd"):
-            args = [0, 0.1, 0.01, 0.9, 0.0, 1.0 if kind.endswith("nesterov") else 0.0, 1.0 if t == 1 else 0.0, 0, 0, 0, 1, 1]
-        else:
-            args = [1 if kind == "adam" else 2, 0.01, 0.01 if kind == "adam" else 0.1, 0, 0, 0, 0, 0.9, 0.999, 1e-8,
-                    1 - 0.9 ** t, 1 - 0.999 ** t]
-        arr = (ctypes.c_float * 16)(*([float(a) for a in args] + [0.0] * (16 - len(args))))
         _launch_all(vg, lambda r, c, s: lib.sdlc_fused_step(
             c._h, 1, gb[r].id, pb[r].id, n, code, ctypes.c_void_p(s1[r].data_ptr()), ctypes.c_void_p(s2[r].data_ptr()),
-            ctypes.c_void_p(master[r].data_ptr()) if dtype != torch.float32 else None, 1.0 / world, arr, s))
+            ctypes.c_void_p(master[r].data_ptr()) if dtype != torch.float32 else None, 1.0 / world,
+            ctypes.c_void_p(hyper[r].data_ptr()), s))
+        _launch_all(vg, lambda r, c, s: lib.sdlc_step_advance(c._h, 1, ctypes.c_void_p(hyper[r].data_ptr()), s))
     tol = 2e-5 if dtype == torch.float32 else 2e-2
     got = [b.tensor(dtype, n).float() for b in pb]
     for gt in got:
