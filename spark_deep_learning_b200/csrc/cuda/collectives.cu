@@ -185,10 +185,13 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint4*>(p) = make_uint4(f_to_bf16x2(f[0], f[1]), f_to_bf16x2(f[2], f[3]), f_to_bf16x2(f[4], f[5]), f_to_bf16x2(f[6], f[7]));
 }
 
-// max over the 16 lanes of a half-warp (xor offsets < 16 never cross the half)
+// max over the 16 lanes of a half-warp.  The two halves of a warp walk different units and may leave their
+// loops at different times, so the shuffle names ONLY the lanes of the caller's half (a full-warp mask
+// would deadlock when the other half has already exited).
 __device__ __forceinline__ float halfwarp_max(float v) {
+  const unsigned mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o));
   return v;
 }
 

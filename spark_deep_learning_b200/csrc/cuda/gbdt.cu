@@ -42,7 +42,7 @@ gbdt_hist_kernel(const uint8_t* __restrict__ bins, const int2* __restrict__ gh, 
 // The build phase wants the whole GPU (one 1024-thread CTA per SM, all co-resident for the local barrier);
 // the cross-rank phase is run by the first `cross_blocks` CTAs only (flag slots exist for kMaxBlocks CTAs).
 constexpr int kHistThreads = 1024;
-__global__ void __launch_bounds__(kHistThreads, 2)
+__global__ void __launch_bounds__(kHistThreads)
 gbdt_hist_allreduce_kernel(CollCtx c, const uint8_t* __restrict__ bins, const int2* __restrict__ gh,
                            const int* __restrict__ pos, long long n, int F, long long hist_elems,
                            unsigned int* grid_ctr, unsigned int grid_epoch, int cross_blocks) {
@@ -143,10 +143,10 @@ int sdlc_gbdt_hist_allreduce(void* h, int channel, int buf, const void* bins, co
   // memset before it and the reads after it
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const CollCtx ctx = c->make_ctx(channel, buf, 0);
-  // every CTA must be co-resident (device-local barrier): two 1024-thread CTAs per SM (32 registers/thread)
+  // every CTA must be co-resident (device-local barrier): exactly one 1024-thread CTA per SM
   int blocks = 0;
   cudaDeviceGetAttribute(&blocks, cudaDevAttrMultiProcessorCount, c->device);
-  blocks = blocks < 1 ? 1 : 2 * blocks;
+  if (blocks < 1) blocks = 1;
   const int cross = blocks < kMaxBlocks ? blocks : kMaxBlocks;
   gbdt_hist_allreduce_kernel<<<blocks, kHistThreads, 0, s>>>(ctx, static_cast<const uint8_t*>(bins), static_cast<const int2*>(gh),
                                                              static_cast<const int*>(pos), n, F, hist_elems,
