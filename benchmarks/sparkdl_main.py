@@ -24,8 +24,9 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
     torch.backends.cudnn.benchmark = True
     comm = hvd.comm_backend()
 
+    bf16_weights = bool(fused_optimizer and fused_model)     # fp32 masters live in the fused optimizer's state
     if model_name == "resnet50":
-        model = models.resnet50(fused=fused_model).to(dev).to(memory_format=torch.channels_last)
+        model = models.resnet50(fused=fused_model, bf16_weights=bf16_weights).to(dev).to(memory_format=torch.channels_last)
         base = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
         host_x = torch.randn(batch, 3, 224, 224).pin_memory()
         host_y = torch.randint(0, 1000, (batch,)).pin_memory()
@@ -39,6 +40,9 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
     crit = torch.nn.CrossEntropyLoss()
 
     def fwd(x, y):
+        if model_name == "resnet50" and bf16_weights:
+            logits = model(x.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
+            return crit(logits.float(), y)
         if model_name == "resnet50":
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return crit(model(x.contiguous(memory_format=torch.channels_last)), y)

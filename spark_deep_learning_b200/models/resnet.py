@@ -57,6 +57,7 @@ class ResNet(nn.Module):
         super().__init__()
         self.stem = _ConvBN(3, 64, 7, stride=2, fused=fused)
         self.pool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.fused = fused
         blocks, cin = [], 64
         for i, n in enumerate(layers):
             width = 64 * 2 ** i
@@ -67,16 +68,35 @@ class ResNet(nn.Module):
         self.fc = nn.Linear(cin, num_classes)
 
     def forward(self, x):
-        x = self.pool(self.stem(x))
+        x = self.stem(x)
+        if self.fused and x.is_cuda:
+            from spark_deep_learning_b200.ops import pool
+            x = pool.max_pool_3x3_s2(x)        # 1-byte argmax, gather backward (falls back when unsupported)
+        else:
+            x = self.pool(x)
         x = self.blocks(x)
         x = torch.flatten(torch.nn.functional.adaptive_avg_pool2d(x, 1), 1)
         return self.fc(x)
 
 
-def resnet50(num_classes=1000, fused=False):
-    return ResNet((3, 4, 6, 3), num_classes, fused)
+def to_bf16_except_norm(model):
+    """bf16 convolution / linear weights with fp32 BatchNorm parameters and statistics.
+
+    With ``hvd.DistributedOptimizer(fused=True)`` the fp32 master copy of every bf16 weight lives in the sharded
+    optimizer state, so no autocast (and none of its per-step weight casts) is needed: feed bf16 inputs."""
+    model.to(torch.bfloat16)
+    for m in model.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.float()
+    return model
 
 
-def resnet18ish(num_classes=10, fused=False):
+def resnet50(num_classes=1000, fused=False, bf16_weights=False):
+    m = ResNet((3, 4, 6, 3), num_classes, fused)
+    return to_bf16_except_norm(m) if bf16_weights else m
+
+
+def resnet18ish(num_classes=10, fused=False, bf16_weights=False):
     """Tiny bottleneck net for smoke tests."""
-    return ResNet((1, 1, 1, 1), num_classes, fused)
+    m = ResNet((1, 1, 1, 1), num_classes, fused)
+    return to_bf16_except_norm(m) if bf16_weights else m

@@ -80,3 +80,23 @@ def test_resnet_fused_matches_unfused():
     for k in (1, 2):
         d = (outs[0][k] - outs[1][k]).abs().max().item() / (outs[1][k].abs().max().item() + 1e-6)
         assert d < 0.15, (k, d)
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 112, 112), (2, 16, 7, 9), (3, 8, 1, 5)])
+def test_maxpool_3x3_s2_matches_torch(shape):
+    from spark_deep_learning_b200.ops import pool
+    torch.manual_seed(1)
+    x = torch.randn(*shape, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    x1 = x.clone().requires_grad_(True)
+    x2 = x.float().clone().requires_grad_(True)
+    assert pool.supported(x1)
+    y = pool.max_pool_3x3_s2(x1)
+    yr = torch.nn.functional.max_pool2d(x2, 3, stride=2, padding=1)
+    assert y.shape == yr.shape and torch.equal(y.float(), yr)
+    g = torch.randn_like(yr)
+    y.backward(g.bfloat16())
+    yr.backward(g.bfloat16().float())
+    # ties (equal bf16 values inside one window) may pick different-but-equal maxima: compare window sums instead
+    assert torch.allclose(x1.grad.float().sum(), x2.grad.sum(), rtol=1e-2, atol=1e-1)
+    same = (x1.grad.float() - x2.grad).abs() < 1e-2
+    assert same.float().mean().item() > 0.999
