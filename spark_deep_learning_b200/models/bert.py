@@ -13,6 +13,7 @@ from torch import nn
 import torch.nn.functional as F
 
 from spark_deep_learning_b200.ops import gemm
+from spark_deep_learning_b200.ops.layernorm import FusedDropoutAddLayerNorm
 
 
 class FusedLinear(nn.Module):
@@ -36,10 +37,10 @@ class Layer(nn.Module):
         self.heads = heads
         self.qkv = FusedLinear(h, 3 * h, fused=fused)
         self.proj = FusedLinear(h, h, fused=fused)
-        self.ln1 = nn.LayerNorm(h, eps=1e-12)
+        self.ln1 = FusedDropoutAddLayerNorm(h, p, eps=1e-12, fused=fused)
         self.up = FusedLinear(h, ffn, act="gelu", fused=fused)
         self.down = FusedLinear(ffn, h, fused=fused)
-        self.ln2 = nn.LayerNorm(h, eps=1e-12)
+        self.ln2 = FusedDropoutAddLayerNorm(h, p, eps=1e-12, fused=fused)
         self.p = p
 
     def forward(self, x):
@@ -47,9 +48,9 @@ class Layer(nn.Module):
         q, k, v = self.qkv(x).view(b, s, 3, self.heads, h // self.heads).permute(2, 0, 3, 1, 4)
         a = F.scaled_dot_product_attention(q, k, v, dropout_p=self.p if self.training else 0.0)
         a = self.proj(a.transpose(1, 2).reshape(b, s, h))
-        x = self.ln1(x + F.dropout(a, self.p, self.training))
+        x = self.ln1(x, a)                       # LayerNorm(x + dropout(a)) in one pass
         f = self.down(self.up(x))
-        return self.ln2(x + F.dropout(f, self.p, self.training))
+        return self.ln2(x, f)
 
 
 class BertForPreTraining(nn.Module):

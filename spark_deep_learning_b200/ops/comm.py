@@ -224,6 +224,8 @@ class SymmComm(object):
         self.staging = self.alloc_symmetric(staging_bytes)
         self._lib.sdlc_comm_set_staging(self._h, 0, self.staging.id)
         self.sync_all()
+        if cfg.autotune and self.world > 1:
+            self.autotune()
 
     def _vote_transport_fallback(self):
         self.transport = "ipc"
@@ -332,6 +334,60 @@ class SymmComm(object):
             n = getattr(self, "_sync_seq", 0)
             self._sync_seq = n + 1
             store_barrier(self.ctx.store, "sync/%d" % n, self.rank, self.world)
+
+    # ---------------------------------------------------------------------------------------------
+    def autotune(self, sizes=(4 << 10, 16 << 10, 64 << 10, 256 << 10, 1 << 20), iters=20):
+        """``SPARKDL_AUTOTUNE=1``: time one-shot vs two-shot/NVLS on this box for a few small
+        sizes, move the one-shot threshold to the measured crossover, and cache the verdict per (world, transport)
+        in ``~/.cache/sparkdl_b200/autotune.json`` so later jobs skip the measurement.  Collective: every rank
+        runs the same launches; rank 0's timing decides (broadcast through the store)."""
+        import json
+        key = "w%d-%s-mc%d" % (self.world, self.transport, int(self.multicast))
+        path = os.path.join(os.path.expanduser("~"), ".cache", "sparkdl_b200", "autotune.json")
+        store = self.ctx.store
+        cached = None
+        if self.rank == 0 and os.path.exists(path):
+            try:
+                cached = json.load(open(path)).get(key)
+            except (OSError, ValueError):
+                cached = None
+        if self.rank == 0:
+            store.set("comm/autotune/cached", cached)
+        cached = store.get("comm/autotune/cached")
+        if cached is None:
+            lib = self._lib
+            s = self.channel_stream(3)
+            ts = torch.cuda.ExternalStream(s, device=torch.device("cuda", self.device))
+            best = 0
+            big_algo = 3 if (self.multicast and self.staging.multicast) else 2
+            for nb in sizes:
+                t = {}
+                for algo in (1, big_algo):
+                    for _ in range(3):
+                        lib.sdlc_allreduce(self._h, 3, self.staging.id, 0, nb // 4, _core.F32, 0, 1.0, 1.0, algo, s)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(ts)
+                    for _ in range(iters):
+                        lib.sdlc_allreduce(self._h, 3, self.staging.id, 0, nb // 4, _core.F32, 0, 1.0, 1.0, algo, s)
+                    e1.record(ts)
+                    ts.synchronize()
+                    t[algo] = e0.elapsed_time(e1) / iters
+                if t[1] <= t[big_algo]:
+                    best = nb
+            cached = {"oneshot_max_bytes": int(best)}
+            if self.rank == 0:
+                store.set("comm/autotune/result", cached)
+                try:
+                    os.makedirs(os.path.dirname(path), exist_ok=True)
+                    allv = json.load(open(path)) if os.path.exists(path) else {}
+                    allv[key] = cached
+                    json.dump(allv, open(path, "w"), indent=1)
+                except (OSError, ValueError):
+                    pass
+            cached = store.get("comm/autotune/result")
+        self._lib.sdlc_comm_set_oneshot_max(self._h, int(cached["oneshot_max_bytes"]))
+        self.autotuned = cached
+        return cached
 
     def engine_executor(self):
         fn = ctypes.cast(self._lib.sdlc_engine_exec, ctypes.c_void_p).value

@@ -135,3 +135,21 @@ def test_smoke_entry():
     out = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "smoke ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.multigpu
+def test_autotune_sets_threshold(monkeypatch, tmp_path):
+    monkeypatch.setenv("SPARKDL_AUTOTUNE", "1")
+    monkeypatch.setenv("HOME", str(tmp_path))
+
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        tuned = hvd.comm_backend().autotuned
+        ok = hvd.allreduce(torch.ones(1000, device="cuda"), op=hvd.Sum)[0].item() == hvd.size()
+        torch.cuda.synchronize()
+        hvd.comm_backend().check_error()
+        return tuned, ok
+    tuned, ok = HorovodRunner(np=-2).run(main)
+    assert ok and "oneshot_max_bytes" in tuned and 0 <= tuned["oneshot_max_bytes"] <= (1 << 20)
