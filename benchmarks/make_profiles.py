@@ -57,12 +57,13 @@ def main():
              "Roofline denominators (%s): HBM copy %.1f GB/s, bf16 GEMM %.1f TFLOP/s burst / %.1f sustained "
              "(`MEASURED_PEAKS.json`); NVLink 770 GB/s measured peer copy / 900 nominal per direction.\n" % (how, hbm, tf_burst, tf_sus),
              "All `ncu` captures: `ncu --set full --clock-control none --import-source on` on one B200 "
-             "(`benchmarks/gpu_call10.sh`, drivers in `benchmarks/ncu_targets.py`); numbers under the profiler are for "
+             "(`benchmarks/gpu_call19.sh`, drivers in `benchmarks/ncu_targets.py`); numbers under the profiler are for "
              "shares and counters only - the timing numbers in the tables further down are CUDA-event timed.\n",
              "## ncu key metrics\n",
              "| report | kernel | time (us) | DRAM rd+wr (MB) | achieved GB/s | %% of %s HBM | tensor pipe %% | regs | grid x block |"
              % how, "|---|---|---|---|---|---|---|---|---|"]
     flops = {"prof_gemm": 2.0 * 8192 * 4096 * 4096, "prof_gemm_bert": 2.0 * 8192 * 4096 * 1024}
+    # prof_allreduce (single GPU, world=1) from an earlier capture is kept only if present
     for rep in sorted(glob.glob(os.path.join(GO, "prof_*.ncu-rep"))):
         name = os.path.basename(rep)[:-8]
         rows, units = ncu_rows(rep)

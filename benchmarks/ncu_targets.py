@@ -71,5 +71,25 @@ def fused_step():
     torch.cuda.synchronize()
 
 
+def ln():
+    from spark_deep_learning_b200.ops import layernorm as L
+    mod = L.FusedDropoutAddLayerNorm(1024, p=0.1).cuda().bfloat16().train()
+    x = torch.randn(64, 128, 1024, device="cuda").bfloat16().requires_grad_(True)
+    a = torch.randn(64, 128, 1024, device="cuda").bfloat16().requires_grad_(True)
+    for _ in range(4):
+        y = mod(x, a)
+        y.backward(torch.ones_like(y))
+    torch.cuda.synchronize()
+
+
+def pool():
+    from spark_deep_learning_b200.ops import pool as P
+    x = torch.randn(256, 64, 112, 112, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    for _ in range(4):
+        y = P.max_pool_3x3_s2(x)
+        y.backward(torch.ones_like(y))
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
-    {"gemm": gemm, "bn": bn, "allreduce": allreduce, "fused_step": fused_step}[sys.argv[1]]()
+    {"gemm": gemm, "bn": bn, "allreduce": allreduce, "fused_step": fused_step, "ln": ln, "pool": pool}[sys.argv[1]]()
