@@ -315,8 +315,6 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             return super(self.__class__, self).zero_grad(set_to_none=set_to_none)
         for b in self._buckets:
             b.flat.zero_()                     # one memset per bucket; a replaced / dropped .grad is re-aliased lazily
-            if set_to_none is None:            # (never true: placeholder keeps the signature honest)
-                continue
         self._zero_calls = getattr(self, "_zero_calls", 0) + 1
         if self._zero_calls <= 2 or self._zero_calls % 64 == 0:
             # periodic full check that every .grad still aliases its bucket (cheap insurance, off the hot path)
