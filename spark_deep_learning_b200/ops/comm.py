@@ -479,29 +479,14 @@ class SymmComm(object):
         gi = opt._bucket_group[b.index]
         group = opt.param_groups[gi]
         dev = torch.device("cuda", self.device)
-        hyper = opt._hyper.get(gi)
-        if hyper is None:
-            vals = [float(v) for v in self.hyper_values(opt, group)] + [0.0] * 7
-            hyper = {"dev": torch.tensor(vals, dtype=torch.float32, device=dev), "lr": float(group["lr"]),
-                     "advanced": False}
-            opt._hyper[gi] = hyper
-        elif float(group["lr"]) != hyper["lr"]:
+        had = gi in opt._hyper
+        hyper = self.fused_hyper(opt, gi)
+        if had and float(group["lr"]) != hyper["lr"]:
             # lr schedulers: refresh the device copy on the producer stream, ordered before the kernel
             hyper["dev"][1].fill_(float(group["lr"]))
             hyper["lr"] = float(group["lr"])
         if st is None:
-            n = lib.sdlc_fused_state_elems(self._h, b.numel, code)
-            st = {"s1": torch.zeros(n, dtype=torch.float32, device=dev), "s2": None, "master": None}
-            if not isinstance(opt, torch.optim.SGD):
-                st["s2"] = torch.zeros(n, dtype=torch.float32, device=dev)
-            if b.dtype != torch.float32:
-                lo = lib.sdlc_fused_slice_start(self._h, b.numel, code)
-                m = torch.zeros(n, dtype=torch.float32, device=dev)
-                avail = max(0, min(n, b.numel - lo))
-                m[:avail] = b.pflat[lo:lo + avail].float()
-                st["master"] = m
-            b.state = st
-            torch.cuda.current_stream(self.device).synchronize()
+            st = self.fused_state(opt, b)
         lib.sdlc_stream_wait_event(s, self.record_ready_event())
         rc = lib.sdlc_fused_step(
             self._h, 1, b.sym.id, b.psym.id, b.numel, code, ctypes.c_void_p(st["s1"].data_ptr()),
@@ -512,6 +497,38 @@ class SymmComm(object):
             raise CommError("fused optimizer step failed: %s" % self._err())
         hyper["advanced"] = False
         return lib.sdlc_record_event(self._h, s)
+
+    def fused_state(self, opt, b):
+        """This rank's shard of the optimizer state of bucket ``b`` (created on first use): fp32 momentum /
+        Adam moments and, for 16-bit parameters, the fp32 master weights of the slice this rank owns."""
+        if b.state is not None:
+            return b.state
+        lib = self._lib
+        code = _TORCH_DTYPE[b.dtype]
+        dev = torch.device("cuda", self.device)
+        n = lib.sdlc_fused_state_elems(self._h, b.numel, code)
+        st = {"s1": torch.zeros(n, dtype=torch.float32, device=dev), "s2": None, "master": None,
+              "lo": lib.sdlc_fused_slice_start(self._h, b.numel, code), "n": n}
+        if not isinstance(opt, torch.optim.SGD):
+            st["s2"] = torch.zeros(n, dtype=torch.float32, device=dev)
+        if b.dtype != torch.float32:
+            m = torch.zeros(n, dtype=torch.float32, device=dev)
+            avail = max(0, min(n, b.numel - st["lo"]))
+            m[:avail] = b.pflat[st["lo"]:st["lo"] + avail].float()
+            st["master"] = m
+        b.state = st
+        torch.cuda.current_stream(self.device).synchronize()
+        return st
+
+    def fused_hyper(self, opt, gi):
+        hyper = opt._hyper.get(gi)
+        if hyper is None:
+            group = opt.param_groups[gi]
+            vals = [float(v) for v in self.hyper_values(opt, group)] + [0.0] * 7
+            hyper = {"dev": torch.tensor(vals, dtype=torch.float32, device=torch.device("cuda", self.device)),
+                     "lr": float(group["lr"]), "advanced": False}
+            opt._hyper[gi] = hyper
+        return hyper
 
     def fused_step_advance(self, opt):
         """After the last bucket of an optimizer step: bump every group's device-side step counter (on the

@@ -208,6 +208,47 @@ def engine_stats():
     return _S.engine.stats()
 
 
+class ProcessSet(object):
+    """Horovod's process-set handle.  One box, one gang: only the global set exists here."""
+
+    def __init__(self, ranks=None):
+        self.ranks = None if ranks is None else list(ranks)
+        self.process_set_id = 0 if ranks is None else None
+
+    def size(self):
+        return size() if self.ranks is None else len(self.ranks)
+
+    def rank(self):
+        return rank() if self.ranks is None else self.ranks.index(rank())
+
+    def included(self):
+        return self.ranks is None or (is_initialized() and rank() in self.ranks)
+
+
+global_process_set = ProcessSet()
+
+
+def add_process_set(process_set):
+    """Sub-communicators are not part of the reference's contract (its only axis is ``np``); refuse loudly."""
+    ranks = process_set.ranks if isinstance(process_set, ProcessSet) else list(process_set)
+    if is_initialized() and sorted(ranks) == list(range(size())):
+        return global_process_set
+    raise NotImplementedError("only the global process set is supported by the single-box sm_100a runtime")
+
+
+def remove_process_set(process_set):  # pylint: disable=unused-argument
+    return False
+
+
+def start_timeline(file_path, mark_cycles=False):  # pylint: disable=unused-argument
+    """The timeline is opened by the engine at ``hvd.init()`` (``HOROVOD_TIMELINE`` / ``SPARKDL_TIMELINE``)."""
+    raise NotImplementedError("set HOROVOD_TIMELINE=<path> before hvd.init(); the C++ engine opens the trace at start-up")
+
+
+def stop_timeline():
+    return None
+
+
 # ---------------------------------------------------------------------------------------------
 # compression (wire dtype != storage dtype; SURVEY.md §2f K6)
 # ---------------------------------------------------------------------------------------------

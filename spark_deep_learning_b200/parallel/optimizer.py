@@ -331,6 +331,53 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                     else:
                         p.grad.zero_()
 
+    # ------------------------------------------------------------------------------------
+    # checkpoint / resume of the fused, sharded state.  Both calls are collective.
+    # ------------------------------------------------------------------------------------
+    def state_dict(self):
+        sd = super(self.__class__, self).state_dict()
+        if not (self._fused and self._buckets):
+            return sd
+        hvd = self._hvd
+        comm = hvd.comm_backend()
+        fused = {"steps": {}, "buckets": []}
+        for gi in sorted({self._bucket_group[b.index] for b in self._buckets}):
+            fused["steps"][gi] = float(comm.fused_hyper(self, gi)["dev"][9].item())
+        for b in self._buckets:
+            st = comm.fused_state(self, b)
+            entry = {"numel": b.numel, "dtype": str(b.dtype)}
+            for k in ("s1", "s2", "master"):
+                if st[k] is None:
+                    entry[k] = None
+                    continue
+                full = hvd.allgather(st[k], name="fused_state.%d.%s" % (b.index, k)) if hvd.size() > 1 else st[k]
+                entry[k] = full[:b.numel].cpu()          # shards are equal-sized and ordered by rank
+            fused["buckets"].append(entry)
+        sd["sparkdl_fused"] = fused
+        return sd
+
+    def load_state_dict(self, state_dict):
+        fused = state_dict.get("sparkdl_fused") if isinstance(state_dict, dict) else None
+        plain = {k: v for k, v in state_dict.items() if k != "sparkdl_fused"}
+        super(self.__class__, self).load_state_dict(plain)
+        if fused is None or not self._fused:
+            return
+        comm = self._hvd.comm_backend()
+        if len(fused["buckets"]) != len(self._buckets):
+            raise ValueError("checkpoint has %d buckets, this optimizer %d (different bucket_bytes?)"
+                             % (len(fused["buckets"]), len(self._buckets)))
+        for b, entry in zip(self._buckets, fused["buckets"]):
+            st = comm.fused_state(self, b)
+            lo, n = st["lo"], st["n"]
+            for k in ("s1", "s2", "master"):
+                if st[k] is None or entry[k] is None:
+                    continue
+                src = entry[k][lo:lo + n].to(st[k].device)
+                st[k].zero_()
+                st[k][:src.numel()].copy_(src)
+        for gi, steps in fused["steps"].items():
+            comm.fused_hyper(self, int(gi))["dev"][9].fill_(float(steps))
+
     def set_backward_passes_per_step(self, passes):
         self.backward_passes_per_step = int(passes)
 

@@ -1,0 +1,49 @@
+"""Unit tests of the C++ host reduction kernels through the C ABI (no processes, no GPU)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from spark_deep_learning_b200.parallel import core
+
+
+@pytest.mark.parametrize("dt,code", [(torch.float32, core.F32), (torch.float64, core.F64), (torch.int32, core.I32),
+                                     (torch.int64, core.I64), (torch.float16, core.F16), (torch.bfloat16, core.BF16),
+                                     (torch.uint8, core.U8)])
+@pytest.mark.parametrize("op,fn", [(core.OP_SUM, torch.add), (core.OP_MIN, torch.minimum), (core.OP_MAX, torch.maximum),
+                                   (core.OP_PRODUCT, torch.mul)])
+def test_reduce_into_matches_torch(dt, code, op, fn):
+    lib = core.load()
+    g = torch.Generator().manual_seed(1)
+    a = (torch.rand(257, generator=g) * 6 + 1).to(dt)
+    b = (torch.rand(257, generator=g) * 6 + 1).to(dt)
+    exp = fn(a.double(), b.double()) if dt.is_floating_point else fn(a, b)
+    got = a.clone()
+    lib.sdl_reduce_into(ctypes.c_void_p(got.data_ptr()), ctypes.c_void_p(b.data_ptr()), 257, code, op)
+    if dt in (torch.float16, torch.bfloat16):
+        assert torch.allclose(got.double(), exp.to(dt).double(), rtol=1e-2, atol=1e-2)
+    else:
+        assert torch.allclose(got.double(), exp.double().to(dt).double() if dt == torch.uint8 else exp.double())
+
+
+def test_half_conversions_round_to_nearest_even():
+    lib = core.load()
+    x = torch.tensor([1.0, 1.0009765625, 65504.0, 6e-8, -2.5, 0.0], dtype=torch.float16)
+    y = torch.zeros_like(x)
+    lib.sdl_reduce_into(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(x.data_ptr()), x.numel(), core.F16, core.OP_SUM)
+    assert torch.equal(y, x)                         # 0 + x must round-trip exactly, incl. subnormals and max
+    b = torch.tensor([1.0, 3.14159, -1e-3, 3e38], dtype=torch.bfloat16)
+    z = torch.zeros_like(b)
+    lib.sdl_reduce_into(ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(b.data_ptr()), b.numel(), core.BF16, core.OP_SUM)
+    assert torch.equal(z, b)
+
+
+def test_scale_buffer():
+    lib = core.load()
+    t = torch.arange(10, dtype=torch.float32)
+    lib.sdl_scale_buffer(ctypes.c_void_p(t.data_ptr()), 10, core.F32, 0.5)
+    assert torch.equal(t, torch.arange(10, dtype=torch.float32) * 0.5)
+    i = torch.arange(10, dtype=torch.int64)
+    lib.sdl_scale_buffer(ctypes.c_void_p(i.data_ptr()), 10, core.I64, 2.0)
+    assert torch.equal(i, torch.arange(10) * 2)

@@ -153,3 +153,64 @@ def test_autotune_sets_threshold(monkeypatch, tmp_path):
         return tuned, ok
     tuned, ok = HorovodRunner(np=-2).run(main)
     assert ok and "oneshot_max_bytes" in tuned and 0 <= tuned["oneshot_max_bytes"] <= (1 << 20)
+
+
+def _resume_main(opt_name):
+    """3 uninterrupted steps == 2 steps + state_dict round trip + 1 step (fused, sharded optimizer state)."""
+    import copy
+    import torch
+    import sparkdl.hvd as hvd
+    hvd.init()
+    r, n = hvd.rank(), hvd.size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(0)
+
+    def make():
+        return torch.nn.Sequential(torch.nn.Linear(32, 257), torch.nn.ReLU(), torch.nn.Linear(257, 8)).to(dev)
+
+    def mkopt(m):
+        base = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9) if opt_name == "sgd" else \
+            torch.optim.AdamW(m.parameters(), lr=1e-2, weight_decay=0.01)
+        return hvd.DistributedOptimizer(base, named_parameters=m.named_parameters(), fused=True, bucket_bytes=20000)
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(8 * n, 32, generator=g).to(dev)[8 * r:8 * r + 8]
+    Y = torch.randn(8 * n, 8, generator=g).to(dev)[8 * r:8 * r + 8]
+
+    def step(m, o):
+        o.zero_grad()
+        ((m(X) - Y) ** 2).mean().backward()
+        o.step()
+    a = make()
+    init = copy.deepcopy(a.state_dict())
+    oa = mkopt(a)
+    hvd.broadcast_parameters(a.state_dict(), 0)
+    for _ in range(3):
+        step(a, oa)
+    b = make()
+    b.load_state_dict(init)
+    ob = mkopt(b)
+    hvd.broadcast_parameters(b.state_dict(), 0)
+    for _ in range(2):
+        step(b, ob)
+    ckpt_model, ckpt_opt = copy.deepcopy(b.state_dict()), ob.state_dict()
+    c = make()
+    oc = mkopt(c)
+    c.load_state_dict(ckpt_model)
+    oc.load_state_dict(ckpt_opt)
+    step(c, oc)
+    torch.cuda.synchronize()
+    hvd.comm_backend().check_error()
+    diff = max((p - q).abs().max().item() for p, q in zip(a.parameters(), c.parameters()))
+    return diff, "sparkdl_fused" in ckpt_opt
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
+def test_fused_optimizer_checkpoint_resume_np1(opt_name):
+    diff, has = HorovodRunner(np=-1).run(_resume_main, opt_name=opt_name)
+    assert has and diff < 1e-5, diff
+
+
+@pytest.mark.multigpu
+def test_fused_optimizer_checkpoint_resume_np2():
+    diff, has = HorovodRunner(np=-2).run(_resume_main, opt_name="adamw")
+    assert has and diff < 1e-5, diff
