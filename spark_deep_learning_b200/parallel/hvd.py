@@ -334,8 +334,32 @@ def _ready_event(t):
     return _S.comm.record_ready_event()
 
 
+_FAULT = {"parsed": False, "kind": None, "rank": -1, "op": -1, "count": 0}
+
+
+def _maybe_fault():
+    """``SPARKDL_FAULT=kill:rank=R:op=K`` / ``raise:rank=R:op=K``: fail rank R at its K-th collective
+    (SURVEY.md §4b T5 - failure detection is tested by injecting the failure mid-training)."""
+    f = _FAULT
+    if not f["parsed"]:
+        f["parsed"] = True
+        spec = os.environ.get("SPARKDL_FAULT", "")
+        parts = spec.split(":")
+        opts = dict(p.split("=", 1) for p in parts[1:] if "=" in p)
+        if parts[0] in ("kill", "raise") and "op" in opts:
+            f.update(kind=parts[0], rank=int(opts.get("rank", -1)), op=int(opts["op"]))
+    if f["kind"] is None or f["rank"] != _S.ctx.rank:
+        return
+    f["count"] += 1
+    if f["count"] == f["op"]:
+        if f["kind"] == "kill":
+            os._exit(137)
+        raise RuntimeError("injected fault on rank %d at collective #%d" % (f["rank"], f["op"]))
+
+
 def _enqueue(req, name, t_in, t_out, op=_core.OP_SUM, root=0, pre=1.0, post=1.0, splits=None,
              shape=None):
+    _maybe_fault()
     return _S.engine.enqueue(req, name, _dtype_code(t_in), _device_of(t_in), op, root,
                              list(t_in.shape if shape is None else shape), pre, post,
                              t_in.data_ptr(), t_out.data_ptr() if t_out is not None else 0,

@@ -81,3 +81,21 @@ def test_log_callback_only_hides_worker_stdout(capfd, monkeypatch):
     HorovodRunner(np=1).run(main)           # np>0 honours driver_log_verbosity
     out = capfd.readouterr().out
     assert "selected line" in out and "noisy worker line" not in out
+
+
+def test_fault_injection_mid_training(monkeypatch):
+    """Rank 1 dies at its 3rd collective: the gang is torn down and the driver raises quickly (no hang)."""
+    monkeypatch.setenv("SPARKDL_FAULT", "kill:rank=1:op=3")
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "0")
+
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        for i in range(10):
+            hvd.allreduce(torch.ones(8), name="step%d" % i)
+        return "finished"
+    t0 = time.time()
+    with pytest.raises(WorkerFailure) as ei:
+        HorovodRunner(np=-2).run(main)
+    assert ei.value.rank == 1 and ei.value.returncode == 137 and time.time() - t0 < 60
