@@ -256,6 +256,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             ev = comm.fused_step_advance(self)
             if ev:
                 comm.current_stream_wait(ev)      # also re-joins the channel stream under graph capture
+        if comm is not None:
+            comm.check_error()                    # a peer-wait timeout of an earlier launch (host-mapped flag, no sync)
         self._synchronized = True
 
     def sync_hyperparams(self):

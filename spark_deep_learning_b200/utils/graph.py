@@ -38,6 +38,7 @@ class GraphedTrainStep(object):
             comm = hvd.comm_backend() if hvd.is_initialized() else None
         except Exception:  # pylint: disable=broad-except
             comm = None
+        self._comm = comm
         n0 = launch_counter.total(comm)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -51,4 +52,6 @@ class GraphedTrainStep(object):
             if torch.is_tensor(t) and t is not s:
                 s.copy_(t, non_blocking=True)
         self.graph.replay()
+        if self._comm is not None:
+            self._comm.check_error()   # in-kernel peer-wait timeouts surface here (host-mapped flag, no sync)
         return self.out

@@ -478,7 +478,10 @@ class _HistBuilder(object):
         return hist.view(n_nodes, self.F, MAX_BINS, 2)
 
 
-DEFAULTS = dict(n_estimators=100, max_depth=6, learning_rate=0.3, gamma=0.0, min_child_weight=1.0, subsample=1.0,
+IGNORED_PARAMS = ("colsample_bylevel", "colsample_bynode", "num_parallel_tree", "monotone_constraints",
+                  "interaction_constraints", "booster", "n_jobs", "importance_type", "max_delta_step", "tree_method")
+
+DEFAULTS = dict(scale_pos_weight=1.0, n_estimators=100, max_depth=6, learning_rate=0.3, gamma=0.0, min_child_weight=1.0, subsample=1.0,
                 colsample_bytree=1.0, reg_lambda=1.0, reg_alpha=0.0, max_bin=256, base_score=0.5, random_state=0,
                 objective=None, num_class=None, early_stopping_rounds=None, eval_metric=None, verbose=False,
                 max_delta_step=0.0, tree_method="hist")
@@ -520,6 +523,14 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
     n, F = X.shape
     w = torch.ones(n, device=device) if weight is None else torch.as_tensor(np.asarray(weight), dtype=torch.float32).to(device)
     objective = p["objective"] or "reg:squarederror"
+    spw = float(p.get("scale_pos_weight") or 1.0)
+    if spw != 1.0 and objective in ("binary:logistic", "reg:logistic"):
+        w = torch.where(y > 0.5, w * spw, w)          # xgboost semantics: positives weigh scale_pos_weight times more
+    non_default = [k for k in IGNORED_PARAMS if params.get(k) not in (None, DEFAULTS.get(k), 1, 1.0, "gbtree", "hist", "gain", 0.0)]
+    if non_default and dist.rank == 0:
+        import warnings
+        warnings.warn("sparkdl.xgboost: parameters accepted for API compatibility but not used by the B200 GBDT engine: %s"
+                      % ", ".join(non_default))
     num_class = int(p["num_class"] or 1)
     obj = _Objective(objective, num_class)
     G = obj.n_groups

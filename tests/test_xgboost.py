@@ -155,3 +155,15 @@ def test_pipeline_and_cross_validator():
     assert cv.bestIndex == 1 and cv.avgMetrics[1] < cv.avgMetrics[0]
     out = Pipeline([reg]).fit(df).transform(df)
     assert "prediction" in out.columns
+
+
+def test_scale_pos_weight_and_ignored_param_warning():
+    X, y = _toy(1500)
+    yb = (y > np.quantile(y, 0.9)).astype(np.float32)          # 10 % positives
+    df = pd.DataFrame({"features": list(X), "label": yb})
+    plain = XgboostClassifier(n_estimators=15, max_depth=3).fit(df).transform(df)
+    heavy = XgboostClassifier(n_estimators=15, max_depth=3, scale_pos_weight=8.0).fit(df).transform(df)
+    rec = lambda o: ((o["prediction"].to_numpy() == 1) & (yb == 1)).sum() / max(1, (yb == 1).sum())  # noqa: E731
+    assert rec(heavy) >= rec(plain)
+    with pytest.warns(UserWarning, match="not used by the B200 GBDT engine"):
+        XgboostRegressor(n_estimators=2, colsample_bylevel=0.5).fit(pd.DataFrame({"features": list(X), "label": y}))
