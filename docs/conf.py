@@ -11,3 +11,5 @@ autoclass_content = "both"
 autodoc_mock_imports = ["tensorflow", "keras", "pyspark"]
 html_theme = "alabaster"
 exclude_patterns = ["_build"]
+templates_path = ["_templates"]
+html_static_path = ["static"]

@@ -10,6 +10,13 @@ from setuptools.command.build_py import build_py
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
+# `python setup.py ... --with-tests` also packages the test-suite (same switch as the reference's setup.py:13-16)
+WITH_TESTS = "--with-tests" in sys.argv
+if WITH_TESTS:
+    sys.argv.remove("--with-tests")
+PACKAGES = ["sparkdl", "sparkdl.*", "spark_deep_learning_b200", "spark_deep_learning_b200.*"] + \
+    (["tests", "tests.*"] if WITH_TESTS else [])
+
 
 class BuildNative(build_py):
     def run(self):
@@ -26,7 +33,7 @@ setup(
     name="sparkdl-b200",
     version="0.1.0",
     description="Blackwell-native HorovodRunner, collectives and xgboost estimators with the sparkdl API",
-    packages=find_packages(include=["sparkdl", "sparkdl.*", "spark_deep_learning_b200", "spark_deep_learning_b200.*"]),
+    packages=find_packages(include=PACKAGES),
     package_data={"spark_deep_learning_b200": ["*.so", "csrc/core/*", "csrc/cuda/*"]},
     python_requires=">=3.9",
     install_requires=["cloudpickle", "numpy", "torch"],
