@@ -6,7 +6,6 @@ hand-written tcgen05 GEMM with the bias / GELU epilogue fused.  Attention itself
 flash kernel behind ``F.scaled_dot_product_attention``.  Parameters are bf16; the fused
 DistributedOptimizer keeps fp32 master weights and Adam moments, sharded 1/N per GPU.
 """
-import math
 
 import torch
 from torch import nn

@@ -99,3 +99,53 @@ def test_fault_injection_mid_training(monkeypatch):
     with pytest.raises(WorkerFailure) as ei:
         HorovodRunner(np=-2).run(main)
     assert ei.value.rank == 1 and ei.value.returncode == 137 and time.time() - t0 < 60
+
+
+def test_np_zero_uses_all_slots_and_warns(monkeypatch, caplog):
+    """np==0 (deprecated, /root/reference/README.md:57-61): every task slot."""
+    import logging
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "2")
+
+    def main():
+        import os
+        return int(os.environ["SPARKDL_SIZE"])
+    with caplog.at_level(logging.WARNING, logger="HorovodRunner"):
+        assert HorovodRunner(np=0).run(main) == 2
+    assert any("deprecated" in r.message for r in caplog.records)
+
+
+def test_driver_log_file_and_kept_job_dir(monkeypatch, tmp_path):
+    """stdout/stderr of every worker is also tee'd into the driver log (ref runner_base.py:49-51)."""
+    log = tmp_path / "driver.log"
+    monkeypatch.setenv("SPARKDL_DRIVER_LOG", str(log))
+
+    def main():
+        import os
+        import sys
+        print("out-%s" % os.environ["SPARKDL_RANK"])
+        sys.stderr.write("err-%s\n" % os.environ["SPARKDL_RANK"])
+        from sparkdl.horovod import log_to_driver
+        log_to_driver("cb-%s" % os.environ["SPARKDL_RANK"])
+    HorovodRunner(np=-2).run(main)
+    text = log.read_text()
+    for needle in ("[0]<stdout> out-0", "[1]<stdout> out-1", "[0]<stderr> err-0", "[1]<stderr> err-1",
+                   "<log_to_driver> cb-0", "<log_to_driver> cb-1"):
+        assert needle in text, needle
+
+
+def test_no_orphan_processes_after_failure():
+    import psutil
+
+    def main():
+        import os
+        import time
+        if os.environ["SPARKDL_RANK"] == "0":
+            raise RuntimeError("rank 0 fails")
+        time.sleep(60)
+    before = {p.pid for p in psutil.Process().children(recursive=True)}
+    with pytest.raises(WorkerFailure):
+        HorovodRunner(np=-3).run(main)
+    time.sleep(0.5)
+    after = [p for p in psutil.Process().children(recursive=True) if p.pid not in before and p.is_running()
+             and p.status() != psutil.STATUS_ZOMBIE]
+    assert not after, after
