@@ -309,7 +309,12 @@ class _Handle(object):
 
 def _auto_name(kind, name):
     if name is not None:
-        return "%s.%s" % (kind, name)
+        full = "%s.%s" % (kind, name)
+        if len(full.encode()) > 120:
+            # the engine's request slots hold 127 name bytes: keep long names unique with a digest suffix
+            import hashlib
+            full = full.encode()[:96].decode("utf-8", "ignore") + "#" + hashlib.sha1(full.encode()).hexdigest()[:20]
+        return full
     n = _S.counters.get(kind, 0)
     _S.counters[kind] = n + 1
     return "%s.noname.%d" % (kind, n)

@@ -260,7 +260,7 @@ class Booster(object):
         base = 0.0 if zero_base else float(obj.base_margin(self.base_score))
         out = torch.full((n, self.n_groups), base, dtype=torch.float32, device=X.device)
         if base_margin is not None:
-            out = torch.as_tensor(base_margin, dtype=torch.float32, device=X.device).reshape(n, -1).clone()
+            out = torch.tensor(np.array(base_margin, dtype=np.float32), device=X.device).reshape(n, -1)
         if not self.trees:
             return out
         p = self._pack(X.device, ntree_limit)

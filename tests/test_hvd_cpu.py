@@ -200,3 +200,15 @@ def test_dead_peer_fails_job_quickly():
         hvd.allreduce(torch.ones(4))      # would hang forever without gang teardown
     with pytest.raises(WorkerFailure):
         HorovodRunner(np=-2).run(main)
+
+
+def test_long_tensor_names_stay_unique():
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        base = "model." + "very_long_submodule_name." * 8           # > 127 bytes, common 127-byte prefix
+        h1 = hvd.allreduce_async(torch.full((2,), 1.0), name=base + "weight", op=hvd.Sum)
+        h2 = hvd.allreduce_async(torch.full((2,), 10.0), name=base + "bias", op=hvd.Sum)
+        return hvd.synchronize(h1)[0].item(), hvd.synchronize(h2)[0].item()
+    assert HorovodRunner(np=-2).run(main) == (2.0, 20.0)
