@@ -34,8 +34,20 @@ void Timeline::open(const std::string& path, int rank) {
   if (f_) fputs("[\n", f_);
 }
 
-void Timeline::event(const std::string& name, const char* phase, char ph, uint64_t ts_us) {
+static std::string json_escape(const std::string& s) {
+  std::string o;
+  o.reserve(s.size());
+  for (char c : s) {
+    if (c == '"' || c == '\\') { o += '\\'; o += c; }
+    else if ((unsigned char)c < 0x20) o += ' ';
+    else o += c;
+  }
+  return o;
+}
+
+void Timeline::event(const std::string& raw_name, const char* phase, char ph, uint64_t ts_us) {
   if (!f_) return;
+  const std::string name = json_escape(raw_name);
   std::lock_guard<std::mutex> g(mu_);
   size_t tid = std::hash<std::string>()(name) % 100000;
   fprintf(f_, "%s{\"name\": \"%s\", \"cat\": \"%s\", \"ph\": \"%c\", \"ts\": %llu, \"pid\": %d, \"tid\": %zu}",

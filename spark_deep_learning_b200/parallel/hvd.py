@@ -336,6 +336,9 @@ def _ready_event(t):
     after the kernels that wrote ``t``."""
     if not t.is_cuda:
         return 0
+    if _S.comm is None:
+        raise ValueError("a CUDA tensor was submitted but this gang runs the CPU-only runtime "
+                         "(no GPU visible at hvd.init(), or SPARKDL_FORCE_CPU=1)")
     return _S.comm.record_ready_event()
 
 
