@@ -1,0 +1,33 @@
+"""docs/ stays consistent with the package (sphinx itself is not installable offline; ref docs/index.rst is the
+authoritative list of public modules)."""
+import importlib
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_conf_is_valid_python_and_names_the_project():
+    ns = {"__file__": os.path.join(ROOT, "docs", "conf.py")}
+    src = open(ns["__file__"]).read()
+    exec(compile(src, ns["__file__"], "exec"), ns)          # pylint: disable=exec-used
+    assert "sphinx.ext.autodoc" in ns["extensions"]
+    assert ns.get("autoclass_content") == "both"
+
+
+def test_every_automodule_imports_and_documents_its_public_names():
+    text = open(os.path.join(ROOT, "docs", "index.rst")).read()
+    mods = re.findall(r"^\.\. automodule:: (\S+)", text, flags=re.M)
+    assert {"sparkdl", "sparkdl.horovod", "sparkdl.horovod.tensorflow.keras", "sparkdl.xgboost"} <= set(mods)
+    for name in mods:
+        m = importlib.import_module(name)
+        for sym in getattr(m, "__all__", []):
+            obj = getattr(m, sym)
+            if callable(obj):
+                assert (obj.__doc__ or "").strip(), "%s.%s has no docstring" % (name, sym)
+
+
+def test_static_assets_referenced_by_the_template_exist():
+    layout = open(os.path.join(ROOT, "docs", "_templates", "layout.html")).read()
+    for asset in re.findall(r"_static/([\w.\-]+)", layout) or re.findall(r"static/([\w.\-]+)", layout):
+        assert os.path.exists(os.path.join(ROOT, "docs", "static", asset)), asset
