@@ -167,3 +167,49 @@ def test_scale_pos_weight_and_ignored_param_warning():
     assert rec(heavy) >= rec(plain)
     with pytest.warns(UserWarning, match="not used by the B200 GBDT engine"):
         XgboostRegressor(n_estimators=2, colsample_bylevel=0.5).fit(pd.DataFrame({"features": list(X), "label": y}))
+
+
+def _three_class_frame(n=900, seed=3):
+    import pandas as pd
+    rng = np.random.RandomState(seed)
+    X = rng.randn(n, 6).astype(np.float32)
+    y = np.argmax(X[:, :3] + 0.3 * rng.randn(n, 3), axis=1).astype(np.float32)
+    return pd.DataFrame({"features": list(X), "label": y})
+
+
+def test_train_validation_split_picks_the_better_map():
+    from spark_deep_learning_b200.xgboost.ml import MulticlassClassificationEvaluator, ParamGridBuilder, TrainValidationSplit
+    df = _three_class_frame()
+    est = XgboostClassifier(n_estimators=8, learning_rate=0.3)
+    grid = ParamGridBuilder().addGrid(est.getParam("max_depth"), [1, 4]).build()
+    m = TrainValidationSplit(est, grid, MulticlassClassificationEvaluator(), trainRatio=0.7, seed=1).fit(df)
+    assert len(m.validationMetrics) == 2 and m.bestIndex == int(np.argmax(m.validationMetrics))
+    acc = float((m.transform(df)["prediction"] == df["label"]).mean())
+    assert acc > 0.8
+
+
+def test_one_vs_rest_matches_native_multiclass_quality():
+    from spark_deep_learning_b200.xgboost.ml import OneVsRest
+    df = _three_class_frame()
+    ovr = OneVsRest(XgboostClassifier(n_estimators=12, max_depth=3, learning_rate=0.3)).fit(df)
+    out = ovr.transform(df)
+    assert len(ovr.models) == 3 and np.stack(out["rawPrediction"].to_list()).shape == (len(df), 3)
+    acc_ovr = float((out["prediction"] == df["label"]).mean())
+    native = XgboostClassifier(n_estimators=12, max_depth=3, learning_rate=0.3).fit(df).transform(df)
+    acc_native = float((native["prediction"] == df["label"]).mean())
+    assert acc_ovr > 0.85 and abs(acc_ovr - acc_native) < 0.08
+
+
+def test_binary_evaluator_auc():
+    import pandas as pd
+    from spark_deep_learning_b200.xgboost.ml import BinaryClassificationEvaluator
+    ev = BinaryClassificationEvaluator()
+    df = pd.DataFrame({"rawPrediction": [[-2.0, 2.0], [-1.0, 1.0], [1.0, -1.0], [0.5, -0.5]], "label": [1, 1, 0, 0]})
+    assert ev.evaluate(df) == 1.0
+    df2 = pd.DataFrame({"rawPrediction": [[0, 1.0], [0, 1.0], [0, 1.0], [0, 1.0]], "label": [1, 0, 1, 0]})
+    assert ev.evaluate(df2) == 0.5                              # all ties
+    rng = np.random.RandomState(0)
+    s, y = rng.randn(300), rng.rand(300) < 0.4
+    s[y] += 1.0
+    pairs = (s[y][:, None] > s[~y][None, :]).mean()
+    assert abs(ev.evaluate(pd.DataFrame({"rawPrediction": [[-v, v] for v in s], "label": y.astype(float)})) - pairs) < 1e-9
