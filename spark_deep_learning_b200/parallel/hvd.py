@@ -595,10 +595,13 @@ def allgather(tensor, name=None, process_set=None):  # pylint: disable=unused-ar
     return synchronize(allgather_async(tensor, name))
 
 
-def grouped_allgather(tensors, name=None, process_set=None):  # pylint: disable=unused-argument
+def grouped_allgather_async(tensors, name=None, process_set=None):  # pylint: disable=unused-argument
     base = _auto_name("grouped_allgather", name)
-    hs = [allgather_async(t, "%s.%d" % (base, i)) for i, t in enumerate(tensors)]
-    return [synchronize(h) for h in hs]
+    return _group([allgather_async(t, "%s.%d" % (base, i)) for i, t in enumerate(tensors)])
+
+
+def grouped_allgather(tensors, name=None, process_set=None):
+    return synchronize(grouped_allgather_async(tensors, name, process_set))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -731,10 +734,13 @@ def reducescatter(tensor, name=None, op=Average, prescale_factor=1.0, postscale_
     return synchronize(reducescatter_async(tensor, name, op, prescale_factor, postscale_factor))
 
 
-def grouped_reducescatter(tensors, name=None, op=Average, process_set=None):  # pylint: disable=unused-argument
+def grouped_reducescatter_async(tensors, name=None, op=Average, process_set=None):  # pylint: disable=unused-argument
     base = _auto_name("grouped_reducescatter", name)
-    hs = [reducescatter_async(t, "%s.%d" % (base, i), op) for i, t in enumerate(tensors)]
-    return [synchronize(h) for h in hs]
+    return _group([reducescatter_async(t, "%s.%d" % (base, i), op) for i, t in enumerate(tensors)])
+
+
+def grouped_reducescatter(tensors, name=None, op=Average, process_set=None):
+    return synchronize(grouped_reducescatter_async(tensors, name, op, process_set))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -849,6 +855,20 @@ def broadcast_optimizer_state(optimizer, root_rank=0, model=None):  # pylint: di
     _require()
     if isinstance(optimizer, torch.optim.LBFGS):
         raise ValueError("cannot broadcast torch.optim.LBFGS state")
+    if getattr(optimizer, "_fused", False) and getattr(optimizer, "_buckets", None):
+        # The fused optimizer's moments / master weights are ONE sharded global copy (its state_dict() is a
+        # collective), so only the plain part travels - plus the checkpoint payload the root loaded since the
+        # last step, which gives the usual "load on rank 0, then broadcast" resume recipe its meaning.
+        payload = None
+        if rank() == root_rank:
+            payload = (torch.optim.Optimizer.state_dict(optimizer), getattr(optimizer, "_pending_fused", None))
+        plain, pending = broadcast_object(payload, root_rank, "optimizer_state")
+        if rank() != root_rank:
+            sd = dict(plain)
+            if pending is not None:
+                sd["sparkdl_fused"] = pending
+            optimizer.load_state_dict(sd)
+        return
     sd = optimizer.state_dict() if rank() == root_rank else None
     sd = broadcast_object(sd, root_rank, "optimizer_state")
     if rank() != root_rank:
@@ -857,3 +877,6 @@ def broadcast_optimizer_state(optimizer, root_rank=0, model=None):  # pylint: di
 
 from spark_deep_learning_b200.parallel.optimizer import DistributedOptimizer  # noqa: E402,F401
 from spark_deep_learning_b200.parallel.sync_batch_norm import SyncBatchNorm  # noqa: E402,F401
+
+
+from spark_deep_learning_b200.parallel import elastic  # noqa: E402  pylint: disable=wrong-import-position

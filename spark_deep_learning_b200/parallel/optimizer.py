@@ -300,6 +300,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             self.synchronize()
         self._reset_step_state()
         self._step_count += 1
+        self._pending_fused = None
         if self._fused:
             loss = closure() if closure is not None else None
             return loss  # the update already happened inside the reduce kernel
@@ -379,6 +380,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 st[k][:src.numel()].copy_(src)
         for gi, steps in fused["steps"].items():
             comm.fused_hyper(self, int(gi))["dev"][9].fill_(float(steps))
+        self._pending_fused = fused               # hvd.broadcast_optimizer_state forwards it; dropped at the next step
 
     def set_backward_passes_per_step(self, passes):
         self.backward_passes_per_step = int(passes)
