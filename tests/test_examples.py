@@ -23,3 +23,10 @@ def test_collectives_tour_cpu():
     r = _run(["examples/collectives_tour.py", "--np", "-2"], env={"SPARKDL_NUM_GPUS": "0", "CUDA_VISIBLE_DEVICES": ""})
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert '"allreduce_sum"' in r.stdout and "tour finished on 2 ranks" in r.stdout
+
+
+def test_all_examples_compile():
+    import py_compile
+    for f in sorted(os.listdir(os.path.join(ROOT, "examples"))):
+        if f.endswith(".py"):
+            py_compile.compile(os.path.join(ROOT, "examples", f), doraise=True)
