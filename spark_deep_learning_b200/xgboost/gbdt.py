@@ -15,6 +15,7 @@ training is bit-reproducible and independent of the worker count.
 import ctypes
 import json
 import math
+import os
 
 import numpy as np
 import torch
@@ -563,6 +564,8 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
     eta, max_depth = float(p["learning_rate"]), int(p["max_depth"])
     start_round = booster.num_boosted_rounds
     arangeF = torch.arange(F, device=device)
+    sibling_subtract = os.environ.get("SPARKDL_GBDT_SIBLING_SUBTRACT", "1") != "0"
+    skip_leaf_hist = os.environ.get("SPARKDL_GBDT_SKIP_LEAF_HIST", "1") != "0"
 
     for it in range(int(p["n_estimators"])):
         g_all, h_all = obj.grad_hess(margin, y, w)
@@ -593,18 +596,40 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                 pos = torch.where(keep, pos, torch.full_like(pos, -1))
             node_of_row = torch.zeros(n, dtype=torch.long, device=device)  # tree node id (for leaf values)
             level_nodes = [0]
+            prev_int = None            # int64 histograms of the previous level (parents of this level's pairs)
+            pair_parent, pair_build_left = [], []
+            child_tot = None           # int64 [nodes, 2] totals of this level, known from the parents' splits
             for depth in range(max_depth + 1):
                 n_nodes = len(level_nodes)
-                hist = builder.build(gh_q, pos, n_nodes).to(torch.float64)
-                hist[..., 0] /= sg
-                hist[..., 1] /= sh
-                tot = hist[:, 0].sum(1)                               # [nodes, 2] totals (feature 0 sees every row)
-                Gt, Ht = tot[:, 0], tot[:, 1]
+                if depth == max_depth and child_tot is not None and skip_leaf_hist:
+                    hist_int, tot_int = None, child_tot                # leaf level: only the totals are needed
+                elif prev_int is not None and sibling_subtract:
+                    # Children come in (left, right) pairs.  Build only the lighter child (by hessian mass - known
+                    # exactly and identically on every worker from the parent's histogram) and derive its sibling
+                    # as parent - built: half the rows, half the atomics, half the allreduce bytes; exact in int64.
+                    n_pairs = n_nodes // 2
+                    build_slots = torch.tensor([2 * j + (0 if pair_build_left[j] else 1) for j in range(n_pairs)], device=device)
+                    other_slots = torch.tensor([2 * j + (1 if pair_build_left[j] else 0) for j in range(n_pairs)], device=device)
+                    lut = torch.full((n_nodes,), -1, dtype=torch.int32, device=device)
+                    lut[build_slots] = torch.arange(n_pairs, dtype=torch.int32, device=device)
+                    pos_build = torch.where(pos >= 0, lut[torch.clamp(pos, min=0).long()], torch.full_like(pos, -1))
+                    built = builder.build(gh_q, pos_build, n_pairs)
+                    hist_int = torch.empty((n_nodes, F, MAX_BINS, 2), dtype=torch.int64, device=device)
+                    hist_int[build_slots] = built
+                    hist_int[other_slots] = prev_int[torch.tensor(pair_parent, device=device)] - built
+                    tot_int = hist_int[:, 0].sum(1)
+                else:
+                    hist_int = builder.build(gh_q, pos, n_nodes)
+                    tot_int = hist_int[:, 0].sum(1)                    # [nodes, 2]: feature 0 sees every row once
+                Gt, Ht = tot_int[:, 0].to(torch.float64) / sg, tot_int[:, 1].to(torch.float64) / sh
                 for s, nid in enumerate(level_nodes):
                     tree.value[nid] = float(-_threshold_l1(Gt[s], alpha) / (Ht[s] + lam) * eta)
                     tree.cover[nid] = float(Ht[s])
                 if depth == max_depth:
                     break
+                hist = hist_int.to(torch.float64)
+                hist[..., 0] /= sg
+                hist[..., 1] /= sh
                 # split search: prefix sums over real bins, missing bin tried on both sides
                 real = hist[:, :, :MISSING_BIN, :]
                 miss = hist[:, :, MISSING_BIN, :]
@@ -637,13 +662,25 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                         best_gain = torch.where(upd, gmax_, best_gain)
                         best_arg = torch.where(upd, arg, best_arg)
                         best_dl = torch.where(upd, torch.full_like(arg, dl), best_dl)
-                bf = (best_arg // MISSING_BIN).tolist()
-                bb = (best_arg % MISSING_BIN).tolist()
+                bf_t, bb_t = best_arg // MISSING_BIN, best_arg % MISSING_BIN
+                bf, bb = bf_t.tolist(), bb_t.tolist()
                 bg = best_gain.tolist()
                 bdl = best_dl.tolist()
+                # exact (integer) totals of the two children of every node under its best split
+                ar = torch.arange(n_nodes, device=device)
+                sel = hist_int[ar, bf_t]                                 # [nodes, 256, 2]
+                left_int = torch.cumsum(sel[:, :MISSING_BIN], 1)[ar, bb_t] + \
+                    torch.where(best_dl.bool().view(-1, 1), sel[:, MISSING_BIN], torch.zeros_like(sel[:, MISSING_BIN]))
+                right_int = tot_int - left_int
+                left_lighter = (left_int[:, 1] <= right_int[:, 1]).tolist()
+                next_tot, pair_parent, pair_build_left = [], [], []
                 next_nodes, slot_feat, slot_bin, slot_dl, slot_left, slot_right = [], [], [], [], [], []
                 for s, nid in enumerate(level_nodes):
                     if bg[s] > 1e-12 and math.isfinite(bg[s]):
+                        pair_parent.append(s)
+                        pair_build_left.append(bool(left_lighter[s]))
+                        next_tot.append(left_int[s])
+                        next_tot.append(right_int[s])
                         l, r = tree.add_node(), tree.add_node()
                         tree.left[nid], tree.right[nid] = l, r
                         tree.feature[nid] = bf[s]
@@ -675,6 +712,8 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                 node_of_row = torch.where(split_here, torch.where(go_left, nl[ps], nr[ps]), node_of_row)
                 pos = torch.where(split_here, new_pos, torch.full_like(pos, -1))
                 level_nodes = next_nodes
+                prev_int = hist_int
+                child_tot = torch.stack(next_tot, 0)
             # leaf assignment for the margin update.  Sub-sampled-out rows were never routed:
             # run them through the finished tree.
             if keep is not None:

@@ -213,3 +213,23 @@ def test_binary_evaluator_auc():
     s[y] += 1.0
     pairs = (s[y][:, None] > s[~y][None, :]).mean()
     assert abs(ev.evaluate(pd.DataFrame({"rawPrediction": [[-v, v] for v in s], "label": y.astype(float)})) - pairs) < 1e-9
+
+
+def test_sibling_subtraction_and_leaf_skip_are_bit_exact(monkeypatch, tmp_path):
+    """Building only the lighter child (+ parent - child) and taking leaf totals from the parent's split must give
+    the very same model as building every node of every level (int64 fixed-point histograms are exact)."""
+    from spark_deep_learning_b200.xgboost import gbdt
+    rng = np.random.RandomState(5)
+    X = rng.randn(3000, 9).astype(np.float32)
+    X[rng.rand(*X.shape) < 0.1] = np.nan
+    y = (np.nan_to_num(X[:, 0]) * np.nan_to_num(X[:, 1]) + 0.2 * rng.randn(3000)).astype(np.float32)
+    dumps, launches = {}, {}
+    for sub in ("0", "1"):
+        for skip in ("0", "1"):
+            monkeypatch.setenv("SPARKDL_GBDT_SIBLING_SUBTRACT", sub)
+            monkeypatch.setenv("SPARKDL_GBDT_SKIP_LEAF_HIST", skip)
+            b, _ = gbdt.train(dict(n_estimators=5, max_depth=4, subsample=0.8, colsample_bytree=0.7), X, y)
+            path = str(tmp_path / ("m%s%s.json" % (sub, skip)))
+            b.save_model(path)
+            dumps[(sub, skip)] = open(path).read()
+    assert len(set(dumps.values())) == 1
