@@ -563,7 +563,10 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
     lam, alpha, gamma, mcw = float(p["reg_lambda"]), float(p["reg_alpha"]), float(p["gamma"]), float(p["min_child_weight"])
     eta, max_depth = float(p["learning_rate"]), int(p["max_depth"])
     start_round = booster.num_boosted_rounds
-    arangeF = torch.arange(F, device=device)
+    arange_n = torch.arange(n, device=device)
+    # bin b of feature f is a split candidate iff b < number of cuts of f
+    bin_has_cut = torch.arange(MISSING_BIN, device=device).view(1, 1, -1) < \
+        torch.tensor([c.numel() for c in cuts], device=device).view(1, F, 1)
     sibling_subtract = os.environ.get("SPARKDL_GBDT_SIBLING_SUBTRACT", "1") != "0"
     skip_leaf_hist = os.environ.get("SPARKDL_GBDT_SKIP_LEAF_HIST", "1") != "0"
 
@@ -647,9 +650,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                     HRd = Ht.view(-1, 1, 1) - HLd
                     gain = 0.5 * (score(GLd, HLd) + score(GRd, HRd) - parent) - gamma
                     ok = (HLd >= mcw) & (HRd >= mcw)
-                    # a cut must exist at this bin: bin b < number of cuts of the feature
-                    ncuts = torch.tensor([c.numel() for c in cuts], device=device).view(1, F, 1)
-                    ok &= torch.arange(MISSING_BIN, device=device).view(1, 1, -1) < ncuts
+                    ok &= bin_has_cut                                    # a cut must exist at this bin
                     if fmask is not None:
                         ok &= fmask.view(1, F, 1)
                     gain = torch.where(ok, gain, torch.full_like(gain, -float("inf")))
@@ -705,7 +706,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                 nr = torch.tensor([tree.right[nid] for nid in level_nodes], device=device)
                 act = pos >= 0
                 ps = torch.clamp(pos, min=0).long()
-                rb = bins[torch.arange(n, device=device), sf[ps]].long()
+                rb = bins[arange_n, sf[ps]].long()
                 go_left = torch.where(rb == MISSING_BIN, sd[ps], rb <= sb[ps])
                 new_pos = torch.where(go_left, sl[ps], sr[ps])
                 split_here = act & (sl[ps] >= 0)
