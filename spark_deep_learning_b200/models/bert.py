@@ -16,6 +16,7 @@ from spark_deep_learning_b200.ops.layernorm import FusedDropoutAddLayerNorm
 
 
 class FusedLinear(nn.Module):
+    """``y = act(x @ W^T + b)`` through the tcgen05 GEMM with the bias/GELU epilogue when ``fused`` and the input is bf16 CUDA."""
     def __init__(self, cin, cout, act=None, fused=True, std=0.02):
         super().__init__()
         self.weight = nn.Parameter(torch.empty(cout, cin).normal_(0, std))
@@ -98,10 +99,12 @@ class BertForPreTraining(nn.Module):
 
 
 def bert_large(fused=True, dtype=torch.bfloat16, **kw):
+    """BERT-large (24 layers, hidden 1024, 16 heads, FFN 4096) for MLM+NSP pre-training."""
     m = BertForPreTraining(fused=fused, **kw)
     return m.to(dtype) if dtype is not None else m
 
 
 def bert_tiny(fused=True, dtype=torch.bfloat16):
+    """2-layer, hidden-128 BERT for smoke tests."""
     m = BertForPreTraining(vocab=1000, hidden=128, layers=2, heads=4, ffn=512, max_pos=64, fused=fused)
     return m.to(dtype) if dtype is not None else m

@@ -92,6 +92,7 @@ def to_bf16_except_norm(model):
 
 
 def resnet50(num_classes=1000, fused=False, bf16_weights=False):
+    """ResNet-50 v1.5; ``fused`` selects the fused BN/ReLU/pool kernels, ``bf16_weights`` bf16 conv/fc weights with fp32 BN."""
     m = ResNet((3, 4, 6, 3), num_classes, fused)
     return to_bf16_except_norm(m) if bf16_weights else m
 

@@ -35,6 +35,7 @@ def _p(t):
 
 
 def supported(x, weight):
+    """True when the fused sm_100a kernel can take these arguments (device, dtype, layout, alignment)."""
     return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
             and x.shape[-1] % 8 == 0 and weight.shape[0] % 8 == 0 and weight.shape[1] == x.shape[-1])
 

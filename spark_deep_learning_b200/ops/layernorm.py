@@ -52,6 +52,7 @@ def _workspace(dev, n):
 
 
 def supported(x, weight):
+    """True when the fused sm_100a kernel can take these arguments (device, dtype, layout, alignment)."""
     return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.is_contiguous()
             and _lib().sdlc_ln_supported(x.shape[-1]) == 1)
 

@@ -46,6 +46,7 @@ def _p(t):
 
 
 def supported(x):
+    """True when the fused sm_100a kernel can take these arguments (device, dtype, layout, alignment)."""
     if not x.is_cuda or x.dim() != 4 or x.dtype not in _DT:
         return False
     if not x.is_contiguous(memory_format=torch.channels_last):

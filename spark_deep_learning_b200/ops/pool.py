@@ -24,6 +24,7 @@ def _lib():
 
 
 def supported(x):
+    """True when the fused sm_100a kernel can take these arguments (device, dtype, layout, alignment)."""
     return (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0
             and x.is_contiguous(memory_format=torch.channels_last))
 
@@ -61,6 +62,7 @@ class _MaxPool3s2(torch.autograd.Function):
 
 
 def max_pool_3x3_s2(x):
+    """3x3 / stride-2 / pad-1 max-pool for NHWC tensors (1-byte argmax, gather backward); falls back to torch when unsupported."""
     if not supported(x):
         return torch.nn.functional.max_pool2d(x, 3, stride=2, padding=1)
     return _MaxPool3s2.apply(x)

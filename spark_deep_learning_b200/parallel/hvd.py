@@ -97,6 +97,7 @@ def init(comm=None, process_sets=None):  # pylint: disable=unused-argument
 
 
 def shutdown():
+    """Drain outstanding operations, stop the engine thread and release the symmetric buffers (idempotent)."""
     with _S.lock:
         if not _S.initialized:
             return
@@ -115,6 +116,7 @@ def shutdown():
 
 
 def is_initialized():
+    """True between ``init()`` and ``shutdown()``."""
     return _S.initialized
 
 
@@ -124,76 +126,93 @@ def _require():
 
 
 def size():
+    """Number of workers in the gang (``np`` of ``HorovodRunner``)."""
     _require()
     return _S.ctx.size
 
 
 def rank():
+    """This worker's rank, ``0 .. size()-1``."""
     _require()
     return _S.ctx.rank
 
 
 def local_rank():
+    """Rank among the workers of this host; equals the GPU index the worker is pinned to."""
     _require()
     return _S.ctx.local_rank
 
 
 def local_size():
+    """Number of workers on this host."""
     _require()
     return _S.ctx.local_size
 
 
 def cross_rank():
+    """Index of this host among the hosts of the job (always 0: single-box runtime)."""
     _require()
     return 0
 
 
 def cross_size():
+    """Number of hosts in the job (always 1: single-box runtime)."""
     _require()
     return 1
 
 
 def is_homogeneous():
+    """True when every host runs the same number of workers (trivially true on one box)."""
     return True
 
 
 def mpi_threads_supported():
+    """Horovod compatibility probe: there is no MPI in this runtime."""
     return False
 
 
 def mpi_enabled():
+    """Horovod compatibility probe: there is no MPI in this runtime."""
     return False
 
 
 def mpi_built():
+    """Horovod compatibility probe: there is no MPI in this runtime."""
     return False
 
 
 def gloo_enabled():
+    """Horovod compatibility probe: the controller is the shm engine, not Gloo."""
     return False
 
 
 def gloo_built():
+    """Horovod compatibility probe: the controller is the shm engine, not Gloo."""
     return False
 
 
 def nccl_built():
+    """Horovod compatibility probe.  GPU collectives are this package's own sm_100a kernels, not NCCL."""
     return 0  # by design: the data plane is our own sm_100a kernels, not NCCL
 
 
 def ddl_built():
+    """Horovod compatibility probe (IBM DDL): always False."""
     return False
 
 
 def ccl_built():
+    """Horovod compatibility probe (oneCCL): always False."""
     return False
 
 
 def cuda_built():
+    """True when a CUDA device is usable by this process."""
     return torch.cuda.is_available()
 
 
 def rocm_built():
+    """Horovod compatibility probe: always False."""
     return False
 
 
@@ -204,6 +223,7 @@ def comm_backend():
 
 
 def engine_stats():
+    """Counters of the C++ engine (responses, fused tensors, stall warnings, ...) as a dict."""
     _require()
     return _S.engine.stats()
 
@@ -237,6 +257,7 @@ def add_process_set(process_set):
 
 
 def remove_process_set(process_set):  # pylint: disable=unused-argument
+    """Process sets other than the global one are not supported; mirrors Horovod's signature."""
     return False
 
 
@@ -246,6 +267,7 @@ def start_timeline(file_path, mark_cycles=False):  # pylint: disable=unused-argu
 
 
 def stop_timeline():
+    """Stop the chrome-trace timeline started by ``start_timeline`` / ``SPARKDL_TIMELINE``."""
     return None
 
 
@@ -449,6 +471,7 @@ def _allreduce_async_impl(tensor, output, name, op, prescale, postscale):
 
 def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.0,
                     postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    """Start an out-of-place allreduce; returns a handle for ``synchronize`` / ``poll``."""
     op = _resolve_op(average, op)
     output = torch.empty_like(tensor, memory_format=torch.contiguous_format)
     return _allreduce_async_impl(tensor, output, _auto_name("allreduce", name), op,
@@ -457,6 +480,7 @@ def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.
 
 def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1.0,
                      postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    """Start an in-place allreduce of ``tensor``; returns a handle for ``synchronize`` / ``poll``."""
     op = _resolve_op(average, op)
     return _allreduce_async_impl(tensor, tensor, _auto_name("allreduce", name), op,
                                  prescale_factor, postscale_factor)
@@ -490,6 +514,7 @@ def allreduce(tensor, average=None, name=None, compression=Compression.none, op=
 
 def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
                process_set=None):  # pylint: disable=unused-argument
+    """In-place allreduce of ``tensor`` (blocking)."""
     return synchronize(allreduce_async_(tensor, average, name, op, prescale_factor, postscale_factor))
 
 
@@ -509,6 +534,7 @@ def grouped_allreduce_async(tensors, average=None, name=None, op=None, prescale_
 
 def grouped_allreduce_async_(tensors, average=None, name=None, op=None, prescale_factor=1.0,
                              postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    """In-place variant of ``grouped_allreduce_async``."""
     op = _resolve_op(average, op)
     base = _auto_name("grouped_allreduce", name)
     subs = [_allreduce_async_impl(t, t, "%s.%d" % (base, i), op, prescale_factor, postscale_factor)
@@ -524,6 +550,7 @@ def _group(subs):
 
 def grouped_allreduce(tensors, average=None, name=None, compression=Compression.none, op=None,
                       prescale_factor=1.0, postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    """Allreduce a list of tensors as one negotiated group (fused into as few launches as possible)."""
     pairs = [compression.compress(t) for t in tensors]
     outs = synchronize(grouped_allreduce_async([p[0] for p in pairs], average, name, op,
                                                prescale_factor, postscale_factor))
@@ -532,6 +559,7 @@ def grouped_allreduce(tensors, average=None, name=None, compression=Compression.
 
 def grouped_allreduce_(tensors, average=None, name=None, op=None, prescale_factor=1.0,
                        postscale_factor=1.0, process_set=None):  # pylint: disable=unused-argument
+    """In-place variant of ``grouped_allreduce``."""
     return synchronize(grouped_allreduce_async_(tensors, average, name, op, prescale_factor,
                                                 postscale_factor))
 
@@ -590,17 +618,20 @@ class _AllgatherFn(torch.autograd.Function):
 
 
 def allgather(tensor, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Concatenate ``tensor`` of every rank along dim 0 (first dimensions may differ); differentiable."""
     if tensor.requires_grad and torch.is_grad_enabled():
         return _AllgatherFn.apply(tensor, name)
     return synchronize(allgather_async(tensor, name))
 
 
 def grouped_allgather_async(tensors, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Start the allgather of every tensor in the list; one handle for the whole group."""
     base = _auto_name("grouped_allgather", name)
     return _group([allgather_async(t, "%s.%d" % (base, i)) for i, t in enumerate(tensors)])
 
 
 def grouped_allgather(tensors, name=None, process_set=None):
+    """Allgather every tensor in the list; returns the list of gathered tensors."""
     return synchronize(grouped_allgather_async(tensors, name, process_set))
 
 
@@ -625,11 +656,13 @@ def _broadcast_async_impl(tensor, output, root_rank, name):
 
 
 def broadcast_async(tensor, root_rank, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Start an out-of-place broadcast from ``root_rank``; returns a handle."""
     output = torch.empty_like(tensor, memory_format=torch.contiguous_format)
     return _broadcast_async_impl(tensor, output, root_rank, _auto_name("broadcast", name))
 
 
 def broadcast_async_(tensor, root_rank, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Start an in-place broadcast from ``root_rank``; returns a handle."""
     return _broadcast_async_impl(tensor, tensor, root_rank, _auto_name("broadcast", name))
 
 
@@ -648,12 +681,14 @@ class _BroadcastFn(torch.autograd.Function):
 
 
 def broadcast(tensor, root_rank, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Return ``root_rank``'s value of ``tensor`` on every rank; differentiable."""
     if tensor.requires_grad and torch.is_grad_enabled():
         return _BroadcastFn.apply(tensor, root_rank, name)
     return synchronize(broadcast_async(tensor, root_rank, name))
 
 
 def broadcast_(tensor, root_rank, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Overwrite ``tensor`` with ``root_rank``'s value (blocking)."""
     return synchronize(broadcast_async_(tensor, root_rank, name))
 
 
@@ -661,6 +696,7 @@ def broadcast_(tensor, root_rank, name=None, process_set=None):  # pylint: disab
 # alltoall / reducescatter
 # ---------------------------------------------------------------------------------------------
 def alltoall_async(tensor, splits=None, name=None, process_set=None):  # pylint: disable=unused-argument
+    """Start an alltoall; ``splits[i]`` rows go to rank i (even split when omitted).  Returns a handle."""
     _require()
     name = _auto_name("alltoall", name)
     src = tensor.contiguous()
@@ -703,6 +739,7 @@ def alltoall(tensor, splits=None, name=None, process_set=None):  # pylint: disab
 
 def reducescatter_async(tensor, name=None, op=Average, prescale_factor=1.0, postscale_factor=1.0,
                         process_set=None):  # pylint: disable=unused-argument
+    """Start a reduce-scatter along dim 0 (rank r keeps the r-th slice of the reduction); returns a handle."""
     _require()
     name = _auto_name("reducescatter", name)
     if op == Average:
@@ -735,11 +772,13 @@ def reducescatter(tensor, name=None, op=Average, prescale_factor=1.0, postscale_
 
 
 def grouped_reducescatter_async(tensors, name=None, op=Average, process_set=None):  # pylint: disable=unused-argument
+    """Start the reduce-scatter of every tensor in the list; one handle for the whole group."""
     base = _auto_name("grouped_reducescatter", name)
     return _group([reducescatter_async(t, "%s.%d" % (base, i), op) for i, t in enumerate(tensors)])
 
 
 def grouped_reducescatter(tensors, name=None, op=Average, process_set=None):
+    """Reduce-scatter every tensor in the list; returns the list of local slices."""
     return synchronize(grouped_reducescatter_async(tensors, name, op, process_set))
 
 
@@ -747,6 +786,7 @@ def grouped_reducescatter(tensors, name=None, op=Average, process_set=None):
 # barrier / join
 # ---------------------------------------------------------------------------------------------
 def barrier(process_set=None):  # pylint: disable=unused-argument
+    """Block until every rank has reached the barrier."""
     _require()
     name = _auto_name("barrier", None)
     h = _S.engine.enqueue(_core.BARRIER, name, _core.U8, -1, 0, 0, [], 1.0, 1.0, 0, 0)

@@ -9,6 +9,7 @@ import numpy as np
 
 
 class Pipeline(object):
+    """Chain of estimators / transformers; ``fit`` returns a ``PipelineModel``."""
     def __init__(self, stages):
         self.stages = list(stages)
 
@@ -26,6 +27,7 @@ class Pipeline(object):
 
 
 class PipelineModel(object):
+    """Fitted pipeline: applies every stage's ``transform`` in order."""
     def __init__(self, stages):
         self.stages = stages
 
@@ -36,6 +38,7 @@ class PipelineModel(object):
 
 
 class ParamGridBuilder(object):
+    """Cartesian product of ``addGrid(param, values)`` as a list of param maps."""
     def __init__(self):
         self._grid = {}
 
@@ -49,6 +52,7 @@ class ParamGridBuilder(object):
 
 
 class RegressionEvaluator(object):
+    """``rmse`` (default) or ``mae`` between ``predictionCol`` and ``labelCol``."""
     def __init__(self, predictionCol="prediction", labelCol="label", metricName="rmse"):
         self.p, self.l, self.m = predictionCol, labelCol, metricName
 
@@ -61,6 +65,7 @@ class RegressionEvaluator(object):
 
 
 class MulticlassClassificationEvaluator(object):
+    """Accuracy of ``predictionCol`` against ``labelCol``."""
     def __init__(self, predictionCol="prediction", labelCol="label", metricName="accuracy"):
         self.p, self.l = predictionCol, labelCol
 
@@ -72,6 +77,7 @@ class MulticlassClassificationEvaluator(object):
 
 
 class CrossValidator(object):
+    """K-fold model selection over ``estimatorParamMaps``; refits the best map on the whole frame."""
     def __init__(self, estimator, estimatorParamMaps, evaluator, numFolds=3, seed=0):
         self.estimator, self.maps, self.evaluator, self.k, self.seed = estimator, estimatorParamMaps, evaluator, numFolds, seed
 
@@ -89,6 +95,7 @@ class CrossValidator(object):
 
 
 class CrossValidatorModel(object):
+    """Result of ``CrossValidator.fit``: ``bestModel``, ``avgMetrics``, ``bestIndex``."""
     def __init__(self, bestModel, avgMetrics, bestIndex):
         self.bestModel, self.avgMetrics, self.bestIndex = bestModel, avgMetrics, bestIndex
 
@@ -143,6 +150,7 @@ class TrainValidationSplit(object):
 
 
 class TrainValidationSplitModel(object):
+    """Result of ``TrainValidationSplit.fit``: ``bestModel``, ``validationMetrics``, ``bestIndex``."""
     def __init__(self, bestModel, validationMetrics, bestIndex):
         self.bestModel, self.validationMetrics, self.bestIndex = bestModel, validationMetrics, bestIndex
 
@@ -172,6 +180,7 @@ class OneVsRest(object):
 
 
 class OneVsRestModel(object):
+    """K binary models; ``transform`` adds the per-class margins and their argmax."""
     def __init__(self, models, predictionCol="prediction", rawPredictionCol="rawPrediction"):
         self.models, self.predictionCol, self.rawPredictionCol = models, predictionCol, rawPredictionCol
 
