@@ -62,6 +62,8 @@ def load():
     lib.sdl_stat_tensors.argtypes = [vp]
     lib.sdl_reduce_into.argtypes = [vp, vp, i64, u32, u32]
     lib.sdl_scale_buffer.argtypes = [vp, i64, u32, dbl]
+    if hasattr(lib, "sdl_gbdt_hist_cpu"):          # absent only in a stale in-tree build
+        lib.sdl_gbdt_hist_cpu.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32]
     _LIB = lib
     return lib
 

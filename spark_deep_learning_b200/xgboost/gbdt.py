@@ -412,6 +412,23 @@ def bin_features(X, cuts, missing):
     return B.contiguous()
 
 
+_CORE_HIST = {"fn": False}
+
+
+def _core_hist_fn():
+    """``sdl_gbdt_hist_cpu`` of libsparkdl_core.so, or None (``SPARKDL_GBDT_NATIVE_CPU=0`` / stale build)."""
+    if _CORE_HIST["fn"] is False:
+        fn = None
+        if os.environ.get("SPARKDL_GBDT_NATIVE_CPU", "1") != "0":
+            try:
+                from spark_deep_learning_b200.parallel import core
+                fn = getattr(core.load(), "sdl_gbdt_hist_cpu", None)
+            except (OSError, RuntimeError):
+                fn = None
+        _CORE_HIST["fn"] = fn
+    return _CORE_HIST["fn"]
+
+
 class _HistBuilder(object):
     """Per-level histogram construction + cross-worker sum."""
 
@@ -463,7 +480,16 @@ class _HistBuilder(object):
             launch_counter.add(1)
             hist = self.dist.allreduce_tensor(hist)
             return hist.view(n_nodes, self.F, MAX_BINS, 2)
-        # CPU: exact integer bincount
+        # CPU: native feature-parallel builder (libsparkdl_core), exact integers
+        native = _core_hist_fn()
+        if native is not None and n_nodes * self.F * MAX_BINS * 2 < (1 << 31):
+            hist = torch.zeros(nelem, dtype=torch.int64)
+            b, q, ps = self.bins.contiguous(), gh_q.contiguous(), pos.contiguous()
+            if native(b.data_ptr(), q.data_ptr(), ps.data_ptr(), hist.data_ptr(), self.n, self.F, n_nodes, 0) != 0:
+                raise RuntimeError("sdl_gbdt_hist_cpu rejected its arguments")
+            hist = self.dist.allreduce_tensor(hist)
+            return hist.view(n_nodes, self.F, MAX_BINS, 2)
+        # fallback: torch index_add_
         act = pos >= 0
         rows = torch.nonzero(act)[:, 0]
         hist = torch.zeros(nelem, dtype=torch.int64)

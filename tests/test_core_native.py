@@ -80,3 +80,30 @@ def test_engine_stress_thread_sanitizer(tmp_path):
     r = subprocess.run([exe, "3", "32"], capture_output=True, text=True, timeout=280, env=env)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
+
+
+def test_native_cpu_histogram_matches_numpy():
+    """sdl_gbdt_hist_cpu (feature-parallel, int64) against a plain numpy scatter-add; bad node ids are rejected."""
+    import numpy as np
+    import torch
+    from spark_deep_learning_b200.parallel import core
+    lib = core.load()
+    rng = np.random.RandomState(0)
+    n, F, nodes = 70000, 11, 5
+    bins = torch.from_numpy(rng.randint(0, 256, size=(n, F)).astype(np.uint8))
+    gh = torch.from_numpy(rng.randint(-2 ** 30, 2 ** 30, size=(n, 2)).astype(np.int32))
+    pos = torch.from_numpy(rng.randint(-1, nodes, size=n).astype(np.int32))
+    hist = torch.zeros(nodes * F * 256 * 2, dtype=torch.int64)
+    assert lib.sdl_gbdt_hist_cpu(bins.data_ptr(), gh.data_ptr(), pos.data_ptr(), hist.data_ptr(), n, F, nodes, 0) == 0
+    ref = np.zeros((nodes, F, 256, 2), dtype=np.int64)
+    act = pos.numpy() >= 0
+    p, b, q = pos.numpy()[act], bins.numpy()[act], gh.numpy()[act].astype(np.int64)
+    for f in range(F):
+        np.add.at(ref[:, f, :, 0], (p, b[:, f]), q[:, 0])
+        np.add.at(ref[:, f, :, 1], (p, b[:, f]), q[:, 1])
+    assert np.array_equal(hist.numpy().reshape(ref.shape), ref)
+    one = torch.zeros_like(hist)                                    # single-threaded path gives the same bits
+    assert lib.sdl_gbdt_hist_cpu(bins.data_ptr(), gh.data_ptr(), pos.data_ptr(), one.data_ptr(), n, F, nodes, 1) == 0
+    assert torch.equal(one, hist)
+    pos[17] = nodes
+    assert lib.sdl_gbdt_hist_cpu(bins.data_ptr(), gh.data_ptr(), pos.data_ptr(), one.data_ptr(), n, F, nodes, 0) == -1

@@ -233,3 +233,21 @@ def test_sibling_subtraction_and_leaf_skip_are_bit_exact(monkeypatch, tmp_path):
             b.save_model(path)
             dumps[(sub, skip)] = open(path).read()
     assert len(set(dumps.values())) == 1
+
+
+def test_native_and_torch_cpu_histograms_give_the_same_model(monkeypatch, tmp_path):
+    from spark_deep_learning_b200.xgboost import gbdt
+    rng = np.random.RandomState(11)
+    X = rng.randn(4000, 7).astype(np.float32)
+    y = (X[:, 0] - X[:, 3] * X[:, 4] + 0.1 * rng.randn(4000)).astype(np.float32)
+    dumps = []
+    for native in ("1", "0"):
+        monkeypatch.setenv("SPARKDL_GBDT_NATIVE_CPU", native)
+        monkeypatch.setitem(gbdt._CORE_HIST, "fn", False)           # re-resolve under the new setting
+        b, _ = gbdt.train(dict(n_estimators=4, max_depth=5), X, y)
+        assert (gbdt._core_hist_fn() is not None) == (native == "1")
+        path = str(tmp_path / ("m%s.json" % native))
+        b.save_model(path)
+        dumps.append(open(path).read())
+    monkeypatch.setitem(gbdt._CORE_HIST, "fn", False)
+    assert dumps[0] == dumps[1]
