@@ -18,6 +18,7 @@ import torch
 
 from spark_deep_learning_b200.parallel import core as _core
 from spark_deep_learning_b200.parallel.store import FdServer, fetch_fd, store_barrier
+from spark_deep_learning_b200.utils import nvtx
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = None
@@ -336,6 +337,7 @@ class SymmComm(object):
             store_barrier(self.ctx.store, "sync/%d" % n, self.rank, self.world)
 
     # ---------------------------------------------------------------------------------------------
+    @nvtx.annotate("sparkdl.autotune")
     def autotune(self, sizes=(4 << 10, 16 << 10, 64 << 10, 256 << 10, 1 << 20), iters=20):
         """``SPARKDL_AUTOTUNE=1``: time one-shot vs two-shot/NVLS on this box for a few small
         sizes, move the one-shot threshold to the measured crossover, and cache the verdict per (world, transport)
@@ -419,6 +421,7 @@ class SymmComm(object):
     # ---------------------------------------------------------------------------------------------
     # collectives on symmetric buffers (hot path; no negotiation, callers guarantee ordering)
     # ---------------------------------------------------------------------------------------------
+    @nvtx.annotate("sparkdl.allreduce")
     def allreduce_symmetric(self, buf, numel, dtype, op=_core.OP_SUM, pre=1.0, post=1.0, wire=None,
                             channel=1, algo="auto", offset_bytes=0, wait_current=True, stream=None):
         """In-place allreduce of a symmetric buffer on the channel's stream.  Returns the raw
@@ -453,6 +456,7 @@ class SymmComm(object):
             self._wire_bufs[key] = wb
         return wb
 
+    @nvtx.annotate("sparkdl.barrier")
     def barrier(self, channel=0):
         if self._lib.sdlc_barrier(self._h, channel, 0):
             raise CommError(self._err())
@@ -470,6 +474,7 @@ class SymmComm(object):
         kind = 2 if isinstance(opt, torch.optim.AdamW) else 1
         return [kind, group["lr"], group["weight_decay"], 0.0, 0.0, 0.0, b1, b2, group["eps"]]
 
+    @nvtx.annotate("sparkdl.fused_step")
     def fused_optimizer_step(self, opt, b, pre, post):
         """Launch the fused reduce-scatter + optimizer + all-gather kernel for bucket ``b``."""
         lib = self._lib
@@ -530,6 +535,7 @@ class SymmComm(object):
             opt._hyper[gi] = hyper
         return hyper
 
+    @nvtx.annotate("sparkdl.fused_step_advance")
     def fused_step_advance(self, opt):
         """After the last bucket of an optimizer step: bump every group's device-side step counter (on the
         channel stream, behind the bucket kernels) and return an event the caller's stream must wait on."""

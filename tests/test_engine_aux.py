@@ -3,6 +3,8 @@ Horovod import shim, config env spellings."""
 import json
 import os
 
+import pytest
+
 from sparkdl import HorovodRunner
 
 
@@ -72,3 +74,23 @@ def test_config_env_spellings(monkeypatch):
     assert cfg.fusion_threshold == 1048576 and cfg.cycle_time_ms == 2.5
     monkeypatch.setenv("SPARKDL_FUSION_THRESHOLD", "2048")   # SPARKDL_ spelling wins
     assert get_config(refresh=True).fusion_threshold == 2048
+
+
+def test_nvtx_annotation_is_free_when_off_and_balanced_when_on(monkeypatch):
+    """SPARKDL_NVTX: off -> the function object is returned untouched; on -> push/pop pairs even when the body raises."""
+    import torch
+    from spark_deep_learning_b200.utils import nvtx
+
+    def body(fail):
+        if fail:
+            raise ValueError("x")
+        return 7
+    assert nvtx.annotate("r", enabled=False)(body) is body
+    calls = []
+    monkeypatch.setattr(torch.cuda.nvtx, "range_push", lambda name: calls.append(name))
+    monkeypatch.setattr(torch.cuda.nvtx, "range_pop", lambda: calls.append(None))
+    wrapped = nvtx.annotate("sparkdl.test", enabled=True)(body)
+    assert wrapped(False) == 7
+    with pytest.raises(ValueError):
+        wrapped(True)
+    assert calls == ["sparkdl.test", None, "sparkdl.test", None]
