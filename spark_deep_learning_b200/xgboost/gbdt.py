@@ -505,13 +505,13 @@ class _HistBuilder(object):
         return hist.view(n_nodes, self.F, MAX_BINS, 2)
 
 
-IGNORED_PARAMS = ("colsample_bylevel", "colsample_bynode", "num_parallel_tree", "monotone_constraints",
-                  "interaction_constraints", "booster", "n_jobs", "importance_type", "max_delta_step", "tree_method")
+IGNORED_PARAMS = ("num_parallel_tree", "interaction_constraints", "booster", "n_jobs", "importance_type", "tree_method")
 
 DEFAULTS = dict(scale_pos_weight=1.0, n_estimators=100, max_depth=6, learning_rate=0.3, gamma=0.0, min_child_weight=1.0, subsample=1.0,
                 colsample_bytree=1.0, reg_lambda=1.0, reg_alpha=0.0, max_bin=256, base_score=0.5, random_state=0,
                 objective=None, num_class=None, early_stopping_rounds=None, eval_metric=None, verbose=False,
-                max_delta_step=0.0, tree_method="hist")
+                max_delta_step=0.0, tree_method="hist", colsample_bylevel=1.0, colsample_bynode=1.0,
+                monotone_constraints=None)
 _ALIASES = {"eta": "learning_rate", "lambda": "reg_lambda", "alpha": "reg_alpha", "seed": "random_state",
             "min_split_loss": "gamma", "num_boost_round": "n_estimators", "verbosity": "verbose"}
 
@@ -523,6 +523,25 @@ def normalize_params(params):
         if v is not None or k in ("objective", "eval_metric", "early_stopping_rounds", "num_class"):
             p[k] = v
     return p
+
+
+def parse_monotone(spec, F, feature_names=None):
+    """``"(1,0,-1)"`` / sequence / ``{feature index or name: c}`` -> list of F ints in {-1, 0, 1}, or None."""
+    if spec is None or spec == "" or spec == "()":
+        return None
+    if isinstance(spec, str):
+        spec = [int(v) for v in spec.strip("()[] ").replace(" ", "").split(",") if v != ""]
+    if isinstance(spec, dict):
+        out = [0] * F
+        for k, v in spec.items():
+            i = feature_names.index(k) if (feature_names and k in feature_names) else int(str(k).lstrip("f"))
+            out[i] = int(v)
+        spec = out
+    spec = [int(v) for v in spec]
+    if len(spec) > F or any(v not in (-1, 0, 1) for v in spec):
+        raise ValueError("monotone_constraints must hold at most %d values from {-1, 0, 1}" % F)
+    spec = spec + [0] * (F - len(spec))
+    return spec if any(spec) else None
 
 
 def _threshold_l1(g, alpha):
@@ -593,6 +612,24 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
     # bin b of feature f is a split candidate iff b < number of cuts of f
     bin_has_cut = torch.arange(MISSING_BIN, device=device).view(1, 1, -1) < \
         torch.tensor([c.numel() for c in cuts], device=device).view(1, F, 1)
+    mds = float(p.get("max_delta_step") or 0.0)
+    mono = parse_monotone(p.get("monotone_constraints"), F)
+    mono_t = torch.tensor(mono, device=device, dtype=torch.float64).view(1, F, 1) if mono else None
+    weighted_gain = mds > 0.0 or mono is not None    # gain from (clamped) child weights instead of the closed form
+    cs_level, cs_node = float(p.get("colsample_bylevel") or 1.0), float(p.get("colsample_bynode") or 1.0)
+    INF = float("inf")
+
+    def leaf_weight(Gx, Hx, lo=None, hi=None):
+        wx = -_threshold_l1(Gx, alpha) / (Hx + lam)
+        if mds > 0.0:
+            wx = wx.clamp(-mds, mds)
+        if lo is not None:
+            wx = torch.maximum(torch.minimum(wx, hi), lo)
+        return wx
+
+    def gain_of_weight(Gx, Hx, wx):                   # -2 * (G w + (H + lambda) w^2 / 2 + alpha |w|)
+        return -(2.0 * Gx * wx + (Hx + lam) * wx * wx + 2.0 * alpha * wx.abs())
+
     sibling_subtract = os.environ.get("SPARKDL_GBDT_SIBLING_SUBTRACT", "1") != "0"
     skip_leaf_hist = os.environ.get("SPARKDL_GBDT_SKIP_LEAF_HIST", "1") != "0"
 
@@ -625,6 +662,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                 pos = torch.where(keep, pos, torch.full_like(pos, -1))
             node_of_row = torch.zeros(n, dtype=torch.long, device=device)  # tree node id (for leaf values)
             level_nodes = [0]
+            node_lo, node_hi = {0: -INF}, {0: INF}      # monotone-constraint weight bounds per tree node
             prev_int = None            # int64 histograms of the previous level (parents of this level's pairs)
             pair_parent, pair_build_left = [], []
             child_tot = None           # int64 [nodes, 2] totals of this level, known from the parents' splits
@@ -651,8 +689,11 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                     hist_int = builder.build(gh_q, pos, n_nodes)
                     tot_int = hist_int[:, 0].sum(1)                    # [nodes, 2]: feature 0 sees every row once
                 Gt, Ht = tot_int[:, 0].to(torch.float64) / sg, tot_int[:, 1].to(torch.float64) / sh
+                lo_t = torch.tensor([node_lo[nid] for nid in level_nodes], device=device, dtype=torch.float64)
+                hi_t = torch.tensor([node_hi[nid] for nid in level_nodes], device=device, dtype=torch.float64)
+                w_node = leaf_weight(Gt, Ht, lo_t, hi_t) if weighted_gain else leaf_weight(Gt, Ht)
                 for s, nid in enumerate(level_nodes):
-                    tree.value[nid] = float(-_threshold_l1(Gt[s], alpha) / (Ht[s] + lam) * eta)
+                    tree.value[nid] = float(w_node[s] * eta)
                     tree.cover[nid] = float(Ht[s])
                 if depth == max_depth:
                     break
@@ -667,18 +708,43 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
 
                 def score(Gx, Hx):
                     return _threshold_l1(Gx, alpha) ** 2 / (Hx + lam)
-                parent = score(Gt, Ht).view(-1, 1, 1)
+                parent = (gain_of_weight(Gt, Ht, w_node) if weighted_gain else score(Gt, Ht)).view(-1, 1, 1)
+                # column sampling below the tree level: same random stream on every worker
+                allowed = fmask if fmask is not None else torch.ones(F, dtype=torch.bool, device=device)
+                if cs_level < 1.0:
+                    cand = torch.nonzero(allowed.cpu())[:, 0]
+                    kl = max(1, int(round(cand.numel() * cs_level)))
+                    lvl = torch.zeros(F, dtype=torch.bool)
+                    lvl[cand[torch.randperm(cand.numel(), generator=rng_cols)[:kl]]] = True
+                    allowed = lvl.to(device)
+                node_mask = None
+                if cs_node < 1.0:
+                    cand = torch.nonzero(allowed.cpu())[:, 0]
+                    kn = max(1, int(round(cand.numel() * cs_node)))
+                    nm = torch.zeros((n_nodes, F), dtype=torch.bool)
+                    for s_ in range(n_nodes):
+                        nm[s_, cand[torch.randperm(cand.numel(), generator=rng_cols)[:kn]]] = True
+                    node_mask = nm.to(device).view(n_nodes, F, 1)
                 best_gain = None
                 for dl in (1, 0):                                        # missing goes left / right
                     GLd = GL + (miss[..., 0:1] if dl else 0)
                     HLd = HL + (miss[..., 1:2] if dl else 0)
                     GRd = Gt.view(-1, 1, 1) - GLd
                     HRd = Ht.view(-1, 1, 1) - HLd
-                    gain = 0.5 * (score(GLd, HLd) + score(GRd, HRd) - parent) - gamma
                     ok = (HLd >= mcw) & (HRd >= mcw)
+                    if weighted_gain:
+                        wl = leaf_weight(GLd, HLd, lo_t.view(-1, 1, 1), hi_t.view(-1, 1, 1))
+                        wr = leaf_weight(GRd, HRd, lo_t.view(-1, 1, 1), hi_t.view(-1, 1, 1))
+                        gain = 0.5 * (gain_of_weight(GLd, HLd, wl) + gain_of_weight(GRd, HRd, wr) - parent) - gamma
+                        if mono_t is not None:
+                            ok &= ~(((mono_t > 0) & (wl > wr)) | ((mono_t < 0) & (wl < wr)))
+                    else:
+                        gain = 0.5 * (score(GLd, HLd) + score(GRd, HRd) - parent) - gamma
                     ok &= bin_has_cut                                    # a cut must exist at this bin
-                    if fmask is not None:
-                        ok &= fmask.view(1, F, 1)
+                    if fmask is not None or cs_level < 1.0:
+                        ok &= allowed.view(1, F, 1)
+                    if node_mask is not None:
+                        ok &= node_mask
                     gain = torch.where(ok, gain, torch.full_like(gain, -float("inf")))
                     flat = gain.view(n_nodes, -1)
                     gmax_, arg = flat.max(1)
@@ -700,6 +766,9 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                     torch.where(best_dl.bool().view(-1, 1), sel[:, MISSING_BIN], torch.zeros_like(sel[:, MISSING_BIN]))
                 right_int = tot_int - left_int
                 left_lighter = (left_int[:, 1] <= right_int[:, 1]).tolist()
+                if mono is not None:
+                    wl_b = leaf_weight(left_int[:, 0].to(torch.float64) / sg, left_int[:, 1].to(torch.float64) / sh, lo_t, hi_t).tolist()
+                    wr_b = leaf_weight(right_int[:, 0].to(torch.float64) / sg, right_int[:, 1].to(torch.float64) / sh, lo_t, hi_t).tolist()
                 next_tot, pair_parent, pair_build_left = [], [], []
                 next_nodes, slot_feat, slot_bin, slot_dl, slot_left, slot_right = [], [], [], [], [], []
                 for s, nid in enumerate(level_nodes):
@@ -710,6 +779,14 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                         next_tot.append(right_int[s])
                         l, r = tree.add_node(), tree.add_node()
                         tree.left[nid], tree.right[nid] = l, r
+                        node_lo[l] = node_lo[r] = node_lo[nid]
+                        node_hi[l] = node_hi[r] = node_hi[nid]
+                        if mono is not None and mono[bf[s]] != 0:
+                            mid = 0.5 * (wl_b[s] + wr_b[s])
+                            if mono[bf[s]] > 0:
+                                node_hi[l], node_lo[r] = min(node_hi[l], mid), max(node_lo[r], mid)
+                            else:
+                                node_lo[l], node_hi[r] = max(node_lo[l], mid), min(node_hi[r], mid)
                         tree.feature[nid] = bf[s]
                         tree.threshold[nid] = float(cuts[bf[s]][bb[s]])
                         tree.default_left[nid] = int(bdl[s])

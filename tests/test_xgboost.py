@@ -166,7 +166,7 @@ def test_scale_pos_weight_and_ignored_param_warning():
     rec = lambda o: ((o["prediction"].to_numpy() == 1) & (yb == 1)).sum() / max(1, (yb == 1).sum())  # noqa: E731
     assert rec(heavy) >= rec(plain)
     with pytest.warns(UserWarning, match="not used by the B200 GBDT engine"):
-        XgboostRegressor(n_estimators=2, colsample_bylevel=0.5).fit(pd.DataFrame({"features": list(X), "label": y}))
+        XgboostRegressor(n_estimators=2, num_parallel_tree=4).fit(pd.DataFrame({"features": list(X), "label": y}))
 
 
 def _three_class_frame(n=900, seed=3):
@@ -251,3 +251,63 @@ def test_native_and_torch_cpu_histograms_give_the_same_model(monkeypatch, tmp_pa
         dumps.append(open(path).read())
     monkeypatch.setitem(gbdt._CORE_HIST, "fn", False)
     assert dumps[0] == dumps[1]
+
+
+def _wiggly(n=3000, seed=0):
+    rng = np.random.RandomState(seed)
+    X = rng.rand(n, 4).astype(np.float32)
+    y = (5 * X[:, 0] + np.sin(10 * np.pi * X[:, 0]) - 5 * X[:, 1] - np.cos(10 * np.pi * X[:, 1]) + 0.3 * rng.randn(n)).astype(np.float32)
+    return X, y
+
+
+@pytest.mark.parametrize("spec", ["(1,-1)", [1, -1, 0, 0], {0: 1, 1: -1}])
+def test_monotone_constraints_are_enforced(spec):
+    """xgboost's monotone_constraints: predictions never decrease in feature 0 / never increase in feature 1."""
+    X, y = _wiggly()
+    df = pd.DataFrame({"features": list(X), "label": y})
+    model = XgboostRegressor(n_estimators=25, max_depth=5, monotone_constraints=spec).fit(df)
+    free = XgboostRegressor(n_estimators=25, max_depth=5).fit(df)
+    grid = np.linspace(0, 1, 150, dtype=np.float32)
+    rng = np.random.RandomState(1)
+
+    def violations(m, f, sign):
+        bad = 0
+        for _ in range(8):
+            Z = np.tile(rng.rand(4).astype(np.float32), (len(grid), 1))
+            Z[:, f] = grid
+            pr = m.transform(pd.DataFrame({"features": list(Z)}))["prediction"].to_numpy()
+            bad += int((np.diff(pr) * sign < -1e-6).sum())
+        return bad
+    assert violations(model, 0, 1) == 0 and violations(model, 1, -1) == 0
+    assert violations(free, 0, 1) > 0                       # the unconstrained fit follows the sine
+    with pytest.raises(ValueError):
+        XgboostRegressor(monotone_constraints="(2,0)").fit(df)
+
+
+def test_max_delta_step_and_column_sampling_below_the_tree_level():
+    from spark_deep_learning_b200.xgboost import gbdt
+    X, y = _wiggly(2000, seed=2)
+    b, _ = gbdt.train(dict(n_estimators=3, max_depth=4, learning_rate=1.0, max_delta_step=0.25), X, y)
+    leaves = [abs(v) for t in b.trees for v, l in zip(t.value, t.left) if l < 0]
+    assert max(leaves) <= 0.25 + 1e-9 and max(leaves) > 0.2
+    base, _ = gbdt.train(dict(n_estimators=6, max_depth=4), X, y)
+    for kw in ({"colsample_bylevel": 0.5}, {"colsample_bynode": 0.5}):
+        m1, _ = gbdt.train(dict(n_estimators=6, max_depth=4, random_state=3, **kw), X, y)
+        m2, _ = gbdt.train(dict(n_estimators=6, max_depth=4, random_state=3, **kw), X, y)
+        assert [t.feature for t in m1.trees] == [t.feature for t in m2.trees]            # seeded -> reproducible
+        assert [t.feature for t in m1.trees] != [t.feature for t in base.trees]          # and it does something
+        pr = np.asarray(m1.predict(X)).ravel()
+        assert np.sqrt(np.mean((pr - y) ** 2)) < 1.5
+
+
+def test_distributed_workers_agree_with_constraints_and_node_sampling(monkeypatch):
+    """The per-level / per-node column draws and the monotone bounds are functions of allreduced data and a shared
+    seed, so two workers still produce the single-worker model."""
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "0")
+    X, y = _wiggly(1200, seed=4)
+    df = pd.DataFrame({"features": list(X), "label": y})
+    kw = dict(n_estimators=6, max_depth=4, monotone_constraints="(1,-1)", colsample_bynode=0.75, colsample_bylevel=0.75,
+              max_delta_step=2.0)
+    single = XgboostRegressor(**kw).fit(df).transform(df)["prediction"].to_numpy()
+    dist = XgboostRegressor(num_workers=2, force_repartition=True, **kw).fit(df).transform(df)["prediction"].to_numpy()
+    assert np.allclose(single, dist, atol=1e-4), np.abs(single - dist).max()
