@@ -32,7 +32,7 @@ _SKLEARN_PARAMS = {
     "colsample_bynode": 1.0, "reg_alpha": 0.0, "reg_lambda": 1.0, "scale_pos_weight": 1.0, "base_score": 0.5,
     "random_state": 0, "num_parallel_tree": 1, "monotone_constraints": None, "interaction_constraints": None,
     "importance_type": "gain", "max_bin": 256, "eval_metric": None, "early_stopping_rounds": None,
-    "verbose": False, "xgb_model": None, "ntree_limit": None, "num_class": None,
+    "verbose": False, "xgb_model": None, "ntree_limit": None, "num_class": None, "tweedie_variance_power": 1.5,
 }
 _UNSUPPORTED = {
     "gpu_id": "use the `use_gpu` param instead",
@@ -262,7 +262,9 @@ class _XgboostModel(Model, _XgboostParams, MLReadable, MLWritable):
     def _transform(self, dataset):
         fr = _Frame(dataset)
         m = self._margins(fr)
-        return fr.with_columns({self.getOrDefault("predictionCol"): m[:, 0].numpy().astype(np.float64)})
+        b = self._xgb_sklearn_model
+        pred = gbdt._Objective(b.objective, b.num_class).transform(m)      # inverse link (identity for squared error)
+        return fr.with_columns({self.getOrDefault("predictionCol"): pred.numpy().astype(np.float64)})
 
     def _save_impl(self, path):
         vals = {p.name: _json_safe(self.getOrDefault(p)) for p in self.params

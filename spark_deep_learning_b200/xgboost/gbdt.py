@@ -31,28 +31,74 @@ def _sigmoid(x):
     return torch.sigmoid(x)
 
 
+_LOGISTIC = ("binary:logistic", "reg:logistic", "binary:logitraw")
+_LOG_LINK = ("count:poisson", "reg:gamma", "reg:tweedie")
+
+
 class _Objective(object):
-    def __init__(self, name, num_class=1):
+    """Gradient / hessian, link function and default metric of the supported xgboost objectives."""
+
+    def __init__(self, name, num_class=1, max_delta_step=0.0, tweedie_variance_power=1.5):
         self.name = name
         self.num_class = num_class if name.startswith("multi:") else 1
+        self.poisson_mds = max_delta_step if max_delta_step > 0 else 0.7      # xgboost's default for count:poisson
+        self.rho = float(tweedie_variance_power)
+        if name == "reg:tweedie" and not 1.0 <= self.rho < 2.0:
+            raise ValueError("tweedie_variance_power must be in [1, 2)")
 
     @property
     def n_groups(self):
         return self.num_class
 
     def base_margin(self, base_score):
-        if self.name in ("binary:logistic", "reg:logistic"):
+        if self.name in _LOGISTIC:
             p = min(max(base_score, 1e-6), 1 - 1e-6)
             return math.log(p / (1 - p))
+        if self.name in _LOG_LINK:
+            return math.log(max(base_score, 1e-16))
         return base_score
 
     def grad_hess(self, margin, y, w):
         if self.name in ("reg:squarederror", "reg:linear"):
             g, h = margin[:, 0] - y, torch.ones_like(y)
             return (g * w).unsqueeze(1), (h * w).unsqueeze(1)
-        if self.name in ("binary:logistic", "reg:logistic"):
+        if self.name in _LOGISTIC:
             p = _sigmoid(margin[:, 0])
             return ((p - y) * w).unsqueeze(1), (torch.clamp(p * (1 - p), min=1e-16) * w).unsqueeze(1)
+        m = margin[:, 0]
+        if self.name == "reg:squaredlogerror":
+            if bool((y <= -1).any()):
+                raise ValueError("reg:squaredlogerror needs labels > -1")
+            p = torch.clamp(m, min=-1 + 1e-6)
+            d = torch.log1p(p) - torch.log1p(y)
+            g, h = d / (p + 1), torch.clamp((1 - d) / (p + 1) ** 2, min=1e-6)
+            return (g * w).unsqueeze(1), (h * w).unsqueeze(1)
+        if self.name == "reg:pseudohubererror":
+            z = m - y
+            sc = 1 + z * z
+            return (z / torch.sqrt(sc) * w).unsqueeze(1), (w / (sc * torch.sqrt(sc))).unsqueeze(1)
+        if self.name == "count:poisson":
+            if bool((y < 0).any()):
+                raise ValueError("count:poisson needs non-negative labels")
+            return ((torch.exp(m) - y) * w).unsqueeze(1), (torch.exp(m + self.poisson_mds) * w).unsqueeze(1)
+        if self.name == "reg:gamma":
+            if bool((y <= 0).any()):
+                raise ValueError("reg:gamma needs positive labels")
+            r = y / torch.exp(m)
+            return ((1 - r) * w).unsqueeze(1), (r * w).unsqueeze(1)
+        if self.name == "reg:tweedie":
+            if bool((y < 0).any()):
+                raise ValueError("reg:tweedie needs non-negative labels")
+            a, b = torch.exp((1 - self.rho) * m), torch.exp((2 - self.rho) * m)
+            g = -y * a + b
+            h = -y * (1 - self.rho) * a + (2 - self.rho) * b
+            return (g * w).unsqueeze(1), (h * w).unsqueeze(1)
+        if self.name == "binary:hinge":
+            t = 2 * y - 1
+            act = m * t < 1
+            g = torch.where(act, -t, torch.zeros_like(m))
+            h = torch.where(act, torch.ones_like(m), torch.full_like(m, 1e-16))
+            return (g * w).unsqueeze(1), (h * w).unsqueeze(1)
         if self.name in ("multi:softprob", "multi:softmax"):
             p = torch.softmax(margin, dim=1)
             onehot = torch.nn.functional.one_hot(y.long(), self.num_class).to(p.dtype)
@@ -62,13 +108,20 @@ class _Objective(object):
     def transform(self, margin):
         if self.name in ("binary:logistic", "reg:logistic"):
             return _sigmoid(margin[:, 0])
+        if self.name in _LOG_LINK:
+            return torch.exp(margin[:, 0])
+        if self.name == "binary:hinge":
+            return (margin[:, 0] > 0).to(margin.dtype)
         if self.name in ("multi:softprob", "multi:softmax"):
             return torch.softmax(margin, dim=1)
         return margin[:, 0]
 
     def default_metric(self):
-        return {"reg:squarederror": "rmse", "reg:linear": "rmse", "binary:logistic": "logloss",
-                "reg:logistic": "rmse", "multi:softprob": "mlogloss", "multi:softmax": "mlogloss"}[self.name]
+        return {"reg:squarederror": "rmse", "reg:linear": "rmse", "binary:logistic": "logloss", "binary:logitraw": "logloss",
+                "reg:logistic": "rmse", "multi:softprob": "mlogloss", "multi:softmax": "mlogloss",
+                "reg:squaredlogerror": "rmsle", "reg:pseudohubererror": "mphe", "count:poisson": "poisson-nloglik",
+                "reg:gamma": "gamma-nloglik", "reg:tweedie": "tweedie-nloglik@%g" % self.rho,
+                "binary:hinge": "error"}[self.name]
 
 
 def _metric_sums(name, obj, margin, y, w):
@@ -83,9 +136,35 @@ def _metric_sums(name, obj, margin, y, w):
     if name == "logloss":
         p = torch.clamp(_sigmoid(margin[:, 0]), eps, 1 - eps)
         return float((-(y * torch.log(p) + (1 - y) * torch.log(1 - p)) * w).sum()), float(w.sum())
-    if name == "error":
-        p = _sigmoid(margin[:, 0])
-        return float((((p > 0.5).to(y.dtype) != y).to(w.dtype) * w).sum()), float(w.sum())
+    if name == "error" or name.startswith("error@"):
+        thr = float(name.split("@", 1)[1]) if "@" in name else 0.5
+        p = obj.transform(margin) if obj.name == "binary:hinge" else _sigmoid(margin[:, 0])
+        return float((((p > thr).to(y.dtype) != y).to(w.dtype) * w).sum()), float(w.sum())
+    if name == "rmsle":
+        pred = torch.clamp(obj.transform(margin), min=-1 + 1e-6)
+        return float(((torch.log1p(pred) - torch.log1p(y)) ** 2 * w).sum()), float(w.sum())
+    if name == "mape":
+        pred = obj.transform(margin)
+        return float((((pred - y) / y).abs() * w).sum()), float(w.sum())
+    if name == "mphe":
+        z = obj.transform(margin) - y
+        return float(((torch.sqrt(1 + z * z) - 1) * w).sum()), float(w.sum())
+    if name == "poisson-nloglik":
+        pred = torch.clamp(obj.transform(margin), min=eps)
+        return float(((pred - y * torch.log(pred) + torch.lgamma(y + 1)) * w).sum()), float(w.sum())
+    if name == "gamma-nloglik":                       # unit dispersion, as in xgboost
+        pred = torch.clamp(obj.transform(margin), min=eps)
+        return float(((y / pred + torch.log(pred)) * w).sum()), float(w.sum())
+    if name == "gamma-deviance":
+        pred = torch.clamp(obj.transform(margin), min=eps)
+        r = torch.clamp(y, min=eps) / pred
+        return float((2 * (r - torch.log(r) - 1) * w).sum()), float(w.sum())
+    if name.startswith("tweedie-nloglik"):
+        rho = float(name.split("@", 1)[1]) if "@" in name else 1.5
+        pred = torch.clamp(obj.transform(margin), min=eps)
+        a = y * torch.pow(pred, 1 - rho) / (1 - rho)
+        b = torch.pow(pred, 2 - rho) / (2 - rho)
+        return float(((-a + b) * w).sum()), float(w.sum())
     if name == "mlogloss":
         p = torch.clamp(torch.softmax(margin, 1), eps, 1.0)
         return float((-torch.log(p.gather(1, y.long().unsqueeze(1)))[:, 0] * w).sum()), float(w.sum())
@@ -96,7 +175,7 @@ def _metric_sums(name, obj, margin, y, w):
 
 def _finish_metric(name, s, n):
     v = s / max(n, 1e-12)
-    return math.sqrt(v) if name == "rmse" else v
+    return math.sqrt(v) if name in ("rmse", "rmsle") else v
 
 
 def _auc(score, y, w):
@@ -511,7 +590,7 @@ DEFAULTS = dict(scale_pos_weight=1.0, n_estimators=100, max_depth=6, learning_ra
                 colsample_bytree=1.0, reg_lambda=1.0, reg_alpha=0.0, max_bin=256, base_score=0.5, random_state=0,
                 objective=None, num_class=None, early_stopping_rounds=None, eval_metric=None, verbose=False,
                 max_delta_step=0.0, tree_method="hist", colsample_bylevel=1.0, colsample_bynode=1.0,
-                monotone_constraints=None)
+                monotone_constraints=None, tweedie_variance_power=1.5)
 _ALIASES = {"eta": "learning_rate", "lambda": "reg_lambda", "alpha": "reg_alpha", "seed": "random_state",
             "min_split_loss": "gamma", "num_boost_round": "n_estimators", "verbosity": "verbose"}
 
@@ -578,7 +657,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
         warnings.warn("sparkdl.xgboost: parameters accepted for API compatibility but not used by the B200 GBDT engine: %s"
                       % ", ".join(non_default))
     num_class = int(p["num_class"] or 1)
-    obj = _Objective(objective, num_class)
+    obj = _Objective(objective, num_class, float(p.get("max_delta_step") or 0.0), float(p.get("tweedie_variance_power") or 1.5))
     G = obj.n_groups
     rng = torch.Generator(device="cpu").manual_seed(int(p["random_state"] or 0) * 1000003 + dist.rank)  # rows: per shard
     rng_cols = torch.Generator(device="cpu").manual_seed(int(p["random_state"] or 0))                  # columns: same everywhere
@@ -613,6 +692,8 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
     bin_has_cut = torch.arange(MISSING_BIN, device=device).view(1, 1, -1) < \
         torch.tensor([c.numel() for c in cuts], device=device).view(1, F, 1)
     mds = float(p.get("max_delta_step") or 0.0)
+    if objective == "count:poisson" and mds == 0.0:
+        mds = 0.7                                     # xgboost's safeguard for the exp link
     mono = parse_monotone(p.get("monotone_constraints"), F)
     mono_t = torch.tensor(mono, device=device, dtype=torch.float64).view(1, F, 1) if mono else None
     weighted_gain = mds > 0.0 or mono is not None    # gain from (clamped) child weights instead of the closed form

@@ -311,3 +311,41 @@ def test_distributed_workers_agree_with_constraints_and_node_sampling(monkeypatc
     single = XgboostRegressor(**kw).fit(df).transform(df)["prediction"].to_numpy()
     dist = XgboostRegressor(num_workers=2, force_repartition=True, **kw).fit(df).transform(df)["prediction"].to_numpy()
     assert np.allclose(single, dist, atol=1e-4), np.abs(single - dist).max()
+
+
+@pytest.mark.parametrize("name", ["reg:squaredlogerror", "reg:pseudohubererror", "reg:gamma", "reg:tweedie", "binary:logitraw"])
+def test_objective_gradients_match_autograd(name):
+    """grad / hess of every closed-form objective equal d/dm and d2/dm2 of its loss (fp64 autograd as the reference)."""
+    import torch
+    from spark_deep_learning_b200.xgboost import gbdt
+    rho = 1.5
+    losses = {
+        "reg:squaredlogerror": lambda m, y: 0.5 * (torch.log1p(m) - torch.log1p(y)) ** 2,
+        "reg:pseudohubererror": lambda m, y: torch.sqrt(1 + (m - y) ** 2) - 1,
+        "reg:gamma": lambda m, y: y / torch.exp(m) + m,
+        "reg:tweedie": lambda m, y: -y * torch.exp((1 - rho) * m) / (1 - rho) + torch.exp((2 - rho) * m) / (2 - rho),
+        "binary:logitraw": lambda m, y: torch.nn.functional.softplus(m) - y * m,
+    }
+    g0 = torch.Generator().manual_seed(0)
+    m = (torch.rand(40, dtype=torch.float64, generator=g0) * 2 + 0.1).requires_grad_()
+    y = (torch.rand(40, dtype=torch.float64, generator=g0) > 0.5).double() if name.startswith("binary") \
+        else torch.rand(40, dtype=torch.float64, generator=g0) * 3 + 0.1
+    g, = torch.autograd.grad(losses[name](m, y).sum(), m, create_graph=True)
+    h = torch.stack([torch.autograd.grad(g[i], m, retain_graph=True)[0][i] for i in range(40)])
+    G, H = gbdt._Objective(name, 1).grad_hess(m.detach().unsqueeze(1), y, torch.ones(40, dtype=torch.float64))
+    assert torch.allclose(G[:, 0], g.detach(), atol=1e-12) and torch.allclose(H[:, 0], h, atol=1e-12)
+
+
+def test_poisson_regression_through_the_estimator():
+    rng = np.random.RandomState(0)
+    X = rng.rand(3000, 4).astype(np.float32)
+    mu = np.exp(0.5 + 1.5 * X[:, 0] - X[:, 1])
+    df = pd.DataFrame({"features": list(X), "label": rng.poisson(mu).astype(np.float32), "isVal": rng.rand(3000) < 0.2})
+    model = XgboostRegressor(objective="count:poisson", n_estimators=40, max_depth=3, learning_rate=0.2,
+                             validationIndicatorCol="isVal").fit(df)
+    pred = model.transform(df)["prediction"].to_numpy()
+    assert pred.min() > 0 and np.corrcoef(pred, mu)[0, 1] > 0.97 and abs(pred.mean() / mu.mean() - 1) < 0.1
+    hist = model._evals_result["validation_0"]["poisson-nloglik"]
+    assert hist[-1] < hist[0]
+    with pytest.raises(Exception, match="non-negative"):
+        XgboostRegressor(objective="count:poisson", n_estimators=1).fit(pd.DataFrame({"features": list(X), "label": -mu}))
