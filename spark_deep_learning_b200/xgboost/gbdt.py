@@ -584,13 +584,13 @@ class _HistBuilder(object):
         return hist.view(n_nodes, self.F, MAX_BINS, 2)
 
 
-IGNORED_PARAMS = ("num_parallel_tree", "interaction_constraints", "booster", "n_jobs", "importance_type", "tree_method")
+IGNORED_PARAMS = ("num_parallel_tree", "booster", "n_jobs", "importance_type", "tree_method")
 
 DEFAULTS = dict(scale_pos_weight=1.0, n_estimators=100, max_depth=6, learning_rate=0.3, gamma=0.0, min_child_weight=1.0, subsample=1.0,
                 colsample_bytree=1.0, reg_lambda=1.0, reg_alpha=0.0, max_bin=256, base_score=0.5, random_state=0,
                 objective=None, num_class=None, early_stopping_rounds=None, eval_metric=None, verbose=False,
                 max_delta_step=0.0, tree_method="hist", colsample_bylevel=1.0, colsample_bynode=1.0,
-                monotone_constraints=None, tweedie_variance_power=1.5)
+                monotone_constraints=None, tweedie_variance_power=1.5, interaction_constraints=None)
 _ALIASES = {"eta": "learning_rate", "lambda": "reg_lambda", "alpha": "reg_alpha", "seed": "random_state",
             "min_split_loss": "gamma", "num_boost_round": "n_estimators", "verbosity": "verbose"}
 
@@ -621,6 +621,33 @@ def parse_monotone(spec, F, feature_names=None):
         raise ValueError("monotone_constraints must hold at most %d values from {-1, 0, 1}" % F)
     spec = spec + [0] * (F - len(spec))
     return spec if any(spec) else None
+
+
+def parse_interactions(spec, F):
+    """``"[[0, 1], [2, 3, 4]]"`` / list of lists of feature indices -> list of frozensets, or None."""
+    if spec is None or spec == "" or spec == "[]":
+        return None
+    if isinstance(spec, str):
+        spec = json.loads(spec)
+    groups = []
+    for grp in spec:
+        g = frozenset(int(str(v).lstrip("f")) for v in grp)
+        if any(v < 0 or v >= F for v in g):
+            raise ValueError("interaction_constraints refer to a feature outside [0, %d)" % F)
+        groups.append(g)
+    return groups or None
+
+
+def _allowed_by_interactions(path, groups, F):
+    """Features a node may split on, given the features already used on its path (xgboost's rule: the path
+    features themselves plus every group that contains the whole path; everything at the root)."""
+    if not path:
+        return None
+    ok = set(path)
+    for g in groups:
+        if path <= g:
+            ok |= g
+    return sorted(ok)
 
 
 def _threshold_l1(g, alpha):
@@ -697,6 +724,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
     mono = parse_monotone(p.get("monotone_constraints"), F)
     mono_t = torch.tensor(mono, device=device, dtype=torch.float64).view(1, F, 1) if mono else None
     weighted_gain = mds > 0.0 or mono is not None    # gain from (clamped) child weights instead of the closed form
+    inter = parse_interactions(p.get("interaction_constraints"), F)
     cs_level, cs_node = float(p.get("colsample_bylevel") or 1.0), float(p.get("colsample_bynode") or 1.0)
     INF = float("inf")
 
@@ -744,6 +772,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
             node_of_row = torch.zeros(n, dtype=torch.long, device=device)  # tree node id (for leaf values)
             level_nodes = [0]
             node_lo, node_hi = {0: -INF}, {0: INF}      # monotone-constraint weight bounds per tree node
+            node_path = {0: frozenset()}                # features used on the way to each node (interaction constraints)
             prev_int = None            # int64 histograms of the previous level (parents of this level's pairs)
             pair_parent, pair_build_left = [], []
             child_tot = None           # int64 [nodes, 2] totals of this level, known from the parents' splits
@@ -806,6 +835,15 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                     for s_ in range(n_nodes):
                         nm[s_, cand[torch.randperm(cand.numel(), generator=rng_cols)[:kn]]] = True
                     node_mask = nm.to(device).view(n_nodes, F, 1)
+                if inter is not None and any(node_path[nid] for nid in level_nodes):
+                    im = torch.ones((n_nodes, F), dtype=torch.bool)
+                    for s_, nid in enumerate(level_nodes):
+                        feats = _allowed_by_interactions(node_path[nid], inter, F)
+                        if feats is not None:
+                            im[s_] = False
+                            im[s_, feats] = True
+                    im = im.to(device).view(n_nodes, F, 1)
+                    node_mask = im if node_mask is None else (node_mask & im)
                 best_gain = None
                 for dl in (1, 0):                                        # missing goes left / right
                     GLd = GL + (miss[..., 0:1] if dl else 0)
@@ -860,6 +898,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                         next_tot.append(right_int[s])
                         l, r = tree.add_node(), tree.add_node()
                         tree.left[nid], tree.right[nid] = l, r
+                        node_path[l] = node_path[r] = node_path[nid] | {bf[s]}
                         node_lo[l] = node_lo[r] = node_lo[nid]
                         node_hi[l] = node_hi[r] = node_hi[nid]
                         if mono is not None and mono[bf[s]] != 0:

@@ -349,3 +349,33 @@ def test_poisson_regression_through_the_estimator():
     assert hist[-1] < hist[0]
     with pytest.raises(Exception, match="non-negative"):
         XgboostRegressor(objective="count:poisson", n_estimators=1).fit(pd.DataFrame({"features": list(X), "label": -mu}))
+
+
+def test_interaction_constraints_limit_the_features_on_every_path():
+    """xgboost's interaction_constraints: features on one root-to-leaf path all come from one group."""
+    from spark_deep_learning_b200.xgboost import gbdt
+    rng = np.random.RandomState(0)
+    X = rng.rand(3000, 5).astype(np.float32)
+    y = (X[:, 0] * X[:, 2] + X[:, 1] * X[:, 3] + X[:, 4] + 0.05 * rng.randn(3000)).astype(np.float32)
+
+    def paths(t):
+        out = []
+
+        def rec(i, acc):
+            if t.left[i] < 0:
+                out.append(frozenset(acc))
+                return
+            rec(t.left[i], acc | {t.feature[i]})
+            rec(t.right[i], acc | {t.feature[i]})
+        rec(0, frozenset())
+        return out
+    free, _ = gbdt.train(dict(n_estimators=10, max_depth=4), X, y)
+    assert any(len(p) > 2 for t in free.trees for p in paths(t))
+    for spec in ("[[0, 2], [1, 3, 4]]", [[0, 1], [2, 3]]):
+        groups = gbdt.parse_interactions(spec, 5)
+        b, _ = gbdt.train(dict(n_estimators=10, max_depth=4, interaction_constraints=spec), X, y)
+        for t in b.trees:
+            for p in paths(t):
+                assert len(p) <= 1 or any(p <= g for g in groups), sorted(p)
+    with pytest.raises(ValueError):
+        gbdt.train(dict(n_estimators=1, interaction_constraints=[[0, 9]]), X, y)
