@@ -179,7 +179,7 @@ def _finish_metric(name, s, n):
 
 
 def _auc(score, y, w):
-    order = torch.argsort(score, descending=True)
+    order = torch.argsort(score, descending=True, stable=True)
     y, w = y[order], w[order]
     tp = torch.cumsum(y * w, 0)
     fp = torch.cumsum((1 - y) * w, 0)
@@ -960,7 +960,12 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
             scores = {}
             for m in metrics:
                 if m == "auc":
-                    scores[m] = _auc(ev["margin"][:, 0], ev["y"], ev["w"])
+                    # rank statistic: needs every worker's validation rows, and every worker must see the SAME value
+                    # (early stopping is decided from it)
+                    cols = torch.stack([ev["margin"][:, 0], ev["y"], ev["w"]], 1).contiguous()
+                    if dist.size > 1:
+                        cols = dist.allgather(cols)
+                    scores[m] = _auc(cols[:, 0], cols[:, 1], cols[:, 2])
                 else:
                     s_, n_ = _metric_sums(m, obj, ev["margin"], ev["y"], ev["w"])
                     s_, n_ = dist.allreduce_host([s_, n_], "sum")
@@ -978,12 +983,18 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                 for cb in callbacks:
                     if callable(cb) and cb({"iteration": rnd, "evals_result": evals_result, "booster": booster}):
                         stop = True
+                if dist.size > 1:                      # a callback that fires on one worker stops all of them
+                    stop = dist.allreduce_host([1.0 if stop else 0.0], "max")[0] > 0
                 if stop:
                     break
             if esr and rnd - best_iter >= int(esr):
                 break
         elif callbacks:
-            if any(callable(cb) and cb({"iteration": rnd, "evals_result": evals_result, "booster": booster}) for cb in callbacks):
+            stop = any([bool(callable(cb) and cb({"iteration": rnd, "evals_result": evals_result, "booster": booster}))
+                        for cb in callbacks])
+            if dist.size > 1:
+                stop = dist.allreduce_host([1.0 if stop else 0.0], "max")[0] > 0
+            if stop:
                 break
     if ev is not None and best is not None:
         booster.best_iteration, booster.best_score = best_iter, best

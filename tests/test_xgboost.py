@@ -379,3 +379,21 @@ def test_interaction_constraints_limit_the_features_on_every_path():
                 assert len(p) <= 1 or any(p <= g for g in groups), sorted(p)
     with pytest.raises(ValueError):
         gbdt.train(dict(n_estimators=1, interaction_constraints=[[0, 9]]), X, y)
+
+
+def test_distributed_auc_early_stopping_is_consistent(monkeypatch):
+    """AUC is a rank statistic: the workers pool their validation rows so that all of them see the same value and
+    take the same early-stopping decision (a per-shard AUC would let them diverge and hang)."""
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "0")
+    rng = np.random.RandomState(7)
+    X = rng.randn(1500, 6).astype(np.float32)
+    yb = ((X[:, 0] + 0.5 * X[:, 1] + 0.8 * rng.randn(1500)) > 0).astype(np.float32)
+    df = pd.DataFrame({"features": list(X), "label": yb, "isVal": rng.rand(1500) < 0.3})
+    kw = dict(n_estimators=60, max_depth=3, learning_rate=0.5, eval_metric="auc", early_stopping_rounds=3,
+              validationIndicatorCol="isVal")
+    single = XgboostClassifier(**kw).fit(df)
+    dist = XgboostClassifier(num_workers=2, **kw).fit(df)
+    bs, bd = single.get_booster(), dist.get_booster()
+    assert bd.num_boosted_rounds < 60                                  # it did stop early
+    assert bs.best_iteration == bd.best_iteration and abs(bs.best_score - bd.best_score) < 1e-6
+    assert np.allclose(single._evals_result["validation_0"]["auc"], dist._evals_result["validation_0"]["auc"], atol=1e-6)
