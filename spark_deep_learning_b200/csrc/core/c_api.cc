@@ -33,6 +33,8 @@ const char* sdl_engine_init(void* e, const char* shm_name, int rank, int world, 
 
 void sdl_engine_shutdown(void* e) { static_cast<Engine*>(e)->shutdown(); }
 void sdl_engine_destroy(void* e) { delete static_cast<Engine*>(e); }
+int sdl_timeline_start(void* e, const char* path) { return static_cast<Engine*>(e)->timeline_start(path ? path : "") ? 0 : -1; }
+void sdl_timeline_stop(void* e) { static_cast<Engine*>(e)->timeline_stop(); }
 void sdl_engine_abort(void* e) { static_cast<Engine*>(e)->shm()->abort_job(); }
 
 void sdl_set_gpu_executor(void* e, void* fn, void* ctx) {

@@ -26,12 +26,18 @@ static const char* type_name(uint32_t t) {
 // Timeline: Chrome-trace JSON, same phase vocabulary as Horovod's HOROVOD_TIMELINE
 // (SURVEY.md §5.1).
 // ------------------------------------------------------------------------------------------
-void Timeline::open(const std::string& path, int rank) {
-  if (path.empty()) return;
+bool Timeline::open(const std::string& path, int rank) {
+  if (path.empty()) return false;
+  std::lock_guard<std::mutex> g(mu_);
+  if (f_.load(std::memory_order_relaxed)) return false;
   std::string p = rank == 0 ? path : path + "." + std::to_string(rank);
-  f_ = fopen(p.c_str(), "w");
+  FILE* f = fopen(p.c_str(), "w");
+  if (!f) return false;
+  fputs("[\n", f);
   rank_ = rank;
-  if (f_) fputs("[\n", f_);
+  first_ = true;
+  f_.store(f, std::memory_order_release);
+  return true;
 }
 
 static std::string json_escape(const std::string& s) {
@@ -46,21 +52,23 @@ static std::string json_escape(const std::string& s) {
 }
 
 void Timeline::event(const std::string& raw_name, const char* phase, char ph, uint64_t ts_us) {
-  if (!f_) return;
+  if (!enabled()) return;
   const std::string name = json_escape(raw_name);
   std::lock_guard<std::mutex> g(mu_);
+  FILE* f = f_.load(std::memory_order_relaxed);
+  if (!f) return;                                  // stopped between the check and the lock
   size_t tid = std::hash<std::string>()(name) % 100000;
-  fprintf(f_, "%s{\"name\": \"%s\", \"cat\": \"%s\", \"ph\": \"%c\", \"ts\": %llu, \"pid\": %d, \"tid\": %zu}",
+  fprintf(f, "%s{\"name\": \"%s\", \"cat\": \"%s\", \"ph\": \"%c\", \"ts\": %llu, \"pid\": %d, \"tid\": %zu}",
           first_ ? "" : ",\n", phase, name.c_str(), ph, (unsigned long long)ts_us, rank_, tid);
   first_ = false;
 }
 
 void Timeline::close() {
-  if (!f_) return;
   std::lock_guard<std::mutex> g(mu_);
-  fputs("\n]\n", f_);
-  fclose(f_);
-  f_ = nullptr;
+  FILE* f = f_.exchange(nullptr, std::memory_order_acq_rel);
+  if (!f) return;
+  fputs("\n]\n", f);
+  fclose(f);
 }
 
 // ------------------------------------------------------------------------------------------

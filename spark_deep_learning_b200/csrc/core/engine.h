@@ -4,6 +4,7 @@
 // different orders; rank 0's engine thread is the coordinator that decides a single global
 // order, so fusion and execution order are identical on every rank.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <map>
@@ -54,13 +55,13 @@ struct Entry {
 
 class Timeline {
  public:
-  void open(const std::string& path, int rank);
+  bool open(const std::string& path, int rank);   // false: empty path, already open, or fopen failed
   void event(const std::string& name, const char* phase, char ph, uint64_t ts_us);
   void close();
-  bool enabled() const { return f_ != nullptr; }
+  bool enabled() const { return f_.load(std::memory_order_acquire) != nullptr; }
 
  private:
-  FILE* f_ = nullptr;
+  std::atomic<FILE*> f_{nullptr};                 // opened / closed at run time (hvd.start_timeline / stop_timeline)
   int rank_ = 0;
   bool first_ = true;
   std::mutex mu_;
@@ -72,6 +73,8 @@ class Engine {
   ~Engine();
   std::string init(const EngineOptions& opt);
   void shutdown();
+  bool timeline_start(const std::string& path) { return timeline_.open(path, opt_.rank); }
+  void timeline_stop() { timeline_.close(); }
   int64_t enqueue(const Request& req, void* in, void* out, int64_t numel, uint64_t ready_event);
   int poll(int64_t handle);
   int wait(int64_t handle, double timeout_s);

@@ -62,6 +62,9 @@ def load():
     lib.sdl_stat_tensors.argtypes = [vp]
     lib.sdl_reduce_into.argtypes = [vp, vp, i64, u32, u32]
     lib.sdl_scale_buffer.argtypes = [vp, i64, u32, dbl]
+    if hasattr(lib, "sdl_timeline_start"):
+        lib.sdl_timeline_start.argtypes = [vp, cp]
+        lib.sdl_timeline_stop.argtypes = [vp]
     if hasattr(lib, "sdl_gbdt_hist_cpu"):          # absent only in a stale in-tree build
         lib.sdl_gbdt_hist_cpu.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32]
     _LIB = lib
@@ -148,6 +151,12 @@ class CoreEngine(object):
     def stats(self):
         return {"responses": self._lib.sdl_stat_responses(self._e),
                 "tensors": self._lib.sdl_stat_tensors(self._e)}
+
+    def timeline_start(self, path):
+        return self._lib.sdl_timeline_start(self._e, path.encode()) == 0
+
+    def timeline_stop(self):
+        self._lib.sdl_timeline_stop(self._e)
 
     def abort(self):
         if self._alive:

@@ -262,13 +262,19 @@ def remove_process_set(process_set):  # pylint: disable=unused-argument
 
 
 def start_timeline(file_path, mark_cycles=False):  # pylint: disable=unused-argument
-    """The timeline is opened by the engine at ``hvd.init()`` (``HOROVOD_TIMELINE`` / ``SPARKDL_TIMELINE``)."""
-    raise NotImplementedError("set HOROVOD_TIMELINE=<path> before hvd.init(); the C++ engine opens the trace at start-up")
+    """Start writing the Chrome-trace timeline of this rank to ``file_path`` (rank r > 0 appends ``.r``).
+
+    Same effect as ``HOROVOD_TIMELINE`` / ``SPARKDL_TIMELINE`` at ``hvd.init()``, but switchable at run time.
+    Raises ``ValueError`` when a timeline is already being recorded or the file cannot be created."""
+    _require()
+    if not _S.engine.timeline_start(str(file_path)):
+        raise ValueError("timeline is already active or %r cannot be opened for writing" % (file_path,))
 
 
 def stop_timeline():
-    """Stop the chrome-trace timeline started by ``start_timeline`` / ``SPARKDL_TIMELINE``."""
-    return None
+    """Stop the chrome-trace timeline started by ``start_timeline`` / ``SPARKDL_TIMELINE`` and close the file."""
+    _require()
+    _S.engine.timeline_stop()
 
 
 # ---------------------------------------------------------------------------------------------

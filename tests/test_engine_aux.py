@@ -94,3 +94,39 @@ def test_nvtx_annotation_is_free_when_off_and_balanced_when_on(monkeypatch):
     with pytest.raises(ValueError):
         wrapped(True)
     assert calls == ["sparkdl.test", None, "sparkdl.test", None]
+
+
+def test_timeline_can_be_started_and_stopped_at_run_time(tmp_path):
+    """hvd.start_timeline / stop_timeline (Horovod's run-time switch): events only while recording, valid JSON, and a
+    second start while active is refused."""
+    path = str(tmp_path / "rt.json")
+
+    def main(path):
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        hvd.allreduce(torch.ones(4), name="before")
+        hvd.start_timeline(path)
+        refused = False
+        try:
+            hvd.start_timeline(path + ".again")
+        except ValueError:
+            refused = True
+        hvd.allreduce(torch.ones(4), name="during")
+        hvd.stop_timeline()
+        hvd.allreduce(torch.ones(4), name="after")
+        hvd.start_timeline(path + ".second")            # restartable
+        hvd.allreduce(torch.ones(4), name="second")
+        hvd.stop_timeline()
+        return refused
+    os.environ["SPARKDL_NUM_GPUS"] = "0"
+    try:
+        assert HorovodRunner(np=-2).run(main, path=path) is True
+    finally:
+        del os.environ["SPARKDL_NUM_GPUS"]
+    for p, inside, outside in ((path, "during", ("before", "after")), (path + ".second", "second", ("during",))):
+        ev = json.load(open(p))
+        names = {e["cat"] for e in ev}
+        assert any(inside in n for n in names), names
+        assert not any(o in n for n in names for o in outside), names
+    assert os.path.exists(path + ".1")                  # rank 1 wrote its own file
