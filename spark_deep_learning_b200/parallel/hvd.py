@@ -405,6 +405,10 @@ def _enqueue(req, name, t_in, t_out, op=_core.OP_SUM, root=0, pre=1.0, post=1.0,
 def poll(handle):
     """True when :func:`synchronize` would not block on the host."""
     _require()
+    if handle.done:
+        return True
+    if not handle.hs and isinstance(handle.keep, list):        # grouped handle: ready when every member is
+        return all(poll(sub) for sub in handle.keep)
     return all(_S.engine.poll(h) != 0 for h in handle.hs)
 
 

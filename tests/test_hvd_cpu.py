@@ -225,7 +225,13 @@ def test_grouped_async_variants_and_elastic_state():
         r, n = hvd.rank(), hvd.size()
         res = {}
         h = hvd.grouped_allgather_async([torch.full((r + 1, k + 1), float(r)) for k in range(3)])
+        import time
+        t0 = time.time()
+        while not hvd.poll(h) and time.time() - t0 < 30:        # a grouped handle polls its members
+            time.sleep(0.001)
+        res["poll_group"] = hvd.poll(h)
         outs = hvd.synchronize(h)
+        res["poll_done"] = hvd.poll(h)
         res["gag"] = [tuple(o.shape) for o in outs] == [(n * (n + 1) // 2, k + 1) for k in range(3)]
         h = hvd.grouped_reducescatter_async([torch.ones(n * 2, 3) * (k + 1) for k in range(2)], op=hvd.Sum)
         outs = hvd.synchronize(h)
