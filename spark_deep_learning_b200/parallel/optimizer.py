@@ -88,6 +88,14 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self._next_launch = 0
         self._hooks = []
         self._fused = bool(fused) and hvd.is_initialized()
+        if self._fused and (hvd.comm_backend() is None
+                            or not all(p.is_cuda for g in self.param_groups for p in g["params"])):
+            # the in-kernel update exists only for CUDA parameters in symmetric buckets: on a CPU gang (or with
+            # CPU parameters) reduce as usual and let the wrapped torch optimizer apply the step
+            import warnings
+            warnings.warn("DistributedOptimizer(fused=True) needs CUDA parameters and the GPU runtime; "
+                          "falling back to allreduce + %s.step()" % type(self).__name__)
+            self._fused = False
         self._hyper = {}          # param-group index -> device hyper-parameter block (fused path)
         self._step_count = 0
         if hvd.is_initialized():

@@ -270,3 +270,28 @@ def test_grouped_async_variants_and_elastic_state():
         return res
     res = HorovodRunner(np=-2).run(main)
     assert all(res.values()), res
+
+
+def test_fused_optimizer_request_on_a_cpu_gang_still_trains():
+    """fused=True has no CPU implementation: it must degrade to allreduce + torch step, never to a silent no-op."""
+    def main():
+        import warnings
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        torch.manual_seed(0)
+        model = torch.nn.Linear(6, 3)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.5), named_parameters=model.named_parameters(),
+                                           fused=True)
+        before = model.weight.detach().clone()
+        x = torch.randn(8, 6, generator=torch.Generator().manual_seed(hvd.rank()))
+        opt.zero_grad()
+        model(x).pow(2).mean().backward()
+        opt.step()
+        moved = (model.weight.detach() - before).abs().max().item()
+        same = hvd.allgather(model.weight.detach().reshape(1, -1))
+        return moved, bool(torch.allclose(same[0], same[-1])), any("falling back" in str(x.message) for x in w)
+    moved, same, warned = HorovodRunner(np=-2).run(main)
+    assert moved > 1e-4 and same and warned
