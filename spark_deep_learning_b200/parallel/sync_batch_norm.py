@@ -23,10 +23,10 @@ class SyncBatchNorm(_BatchNorm):
                 self.weight, self.bias, self.training, self._momentum(), self.eps)
         c = input.shape[1]
         dims = [0] + list(range(2, input.dim()))
-        x = input.float()
+        x = input.float() if input.dtype in (torch.float16, torch.bfloat16) else input   # fp64 stays fp64
         n_local = x.numel() // c
         stats = torch.cat([x.sum(dims), (x * x).sum(dims),
-                           torch.full((1,), float(n_local), device=x.device)])
+                           torch.full((1,), float(n_local), device=x.device, dtype=x.dtype)])
         stats = hvd.allreduce(stats, op=hvd.Sum, name=None)
         n = stats[2 * c]
         mean = stats[:c] / n
@@ -41,7 +41,7 @@ class SyncBatchNorm(_BatchNorm):
         shape = [1, c] + [1] * (input.dim() - 2)
         y = (x - mean.view(shape)) * torch.rsqrt(var.view(shape) + self.eps)
         if self.affine:
-            y = y * self.weight.view(shape).float() + self.bias.view(shape).float()
+            y = y * self.weight.view(shape).to(x.dtype) + self.bias.view(shape).to(x.dtype)
         return y.to(input.dtype)
 
     def _momentum(self):

@@ -295,3 +295,39 @@ def test_fused_optimizer_request_on_a_cpu_gang_still_trains():
         return moved, bool(torch.allclose(same[0], same[-1])), any("falling back" in str(x.message) for x in w)
     moved, same, warned = HorovodRunner(np=-2).run(main)
     assert moved > 1e-4 and same and warned
+
+
+def test_sync_batch_norm_matches_full_batch_batch_norm():
+    """hvd.SyncBatchNorm over 2 workers x half a batch == nn.BatchNorm2d over the whole batch: outputs, input gradients,
+    parameter gradients (after the sum over workers) and running statistics."""
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        r, n = hvd.rank(), hvd.size()
+        g = torch.Generator().manual_seed(0)
+        X = torch.randn(4 * n, 3, 5, 5, generator=g, dtype=torch.float64)
+        W = torch.randn(4 * n, 3, 5, 5, generator=g, dtype=torch.float64)      # loss = sum(y * W)
+        ref = torch.nn.BatchNorm2d(3).double()
+        with torch.no_grad():
+            ref.weight.copy_(torch.tensor([1.5, 0.5, -1.0]))
+            ref.bias.copy_(torch.tensor([0.1, -0.2, 0.3]))
+        sbn = hvd.SyncBatchNorm(3).double()
+        sbn.load_state_dict(ref.state_dict())
+        xr = X.clone().requires_grad_()
+        yr = ref(xr)                                    # exactly one training-mode forward (running stats update once)
+        (yr * W).sum().backward()
+        xl = X[4 * r:4 * r + 4].clone().requires_grad_()
+        yl = sbn(xl)
+        (yl * W[4 * r:4 * r + 4]).sum().backward()
+        wg = hvd.allreduce(sbn.weight.grad, op=hvd.Sum)
+        bg = hvd.allreduce(sbn.bias.grad, op=hvd.Sum)
+        return {
+            "y": bool(torch.allclose(yl, yr[4 * r:4 * r + 4].detach(), atol=1e-10)),
+            "dx": bool(torch.allclose(xl.grad, xr.grad[4 * r:4 * r + 4], atol=1e-10)),
+            "dw": bool(torch.allclose(wg, ref.weight.grad, atol=1e-9)) and bool(torch.allclose(bg, ref.bias.grad, atol=1e-9)),
+            "rm": bool(torch.allclose(sbn.running_mean, ref.running_mean, atol=1e-10)),
+            "rv": bool(torch.allclose(sbn.running_var, ref.running_var, atol=1e-10)),
+        }
+    res = HorovodRunner(np=-2).run(main)
+    assert all(res.values()), res
