@@ -331,3 +331,88 @@ def test_sync_batch_norm_matches_full_batch_batch_norm():
         }
     res = HorovodRunner(np=-2).run(main)
     assert all(res.values()), res
+
+
+def test_optimizer_recipes_and_differentiable_collectives():
+    """Gradient accumulation (backward_passes_per_step), the clipping recipe (synchronize + skip_synchronize),
+    gradient_predivide_factor, compression, in-place grouped allreduce, process-set stubs, Adasum refusal and the
+    autograd rules of allreduce / allgather / broadcast."""
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        r, n = hvd.rank(), hvd.size()
+        res = {}
+
+        def make():
+            torch.manual_seed(1)
+            return torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 2))
+        gen = torch.Generator().manual_seed(9)
+        X, Y = torch.randn(8 * n, 5, generator=gen), torch.randn(8 * n, 2, generator=gen)
+
+        # (1) accumulation over 2 micro-batches + predivide: equals one big-batch SGD step on the global mean loss
+        model, ref = make(), make()
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.2), named_parameters=model.named_parameters(),
+                                       backward_passes_per_step=2, gradient_predivide_factor=2.0, bucket_bytes=64)
+        opt.zero_grad()
+        for k in range(2):
+            lo = 8 * r + 4 * k
+            ((model(X[lo:lo + 4]) - Y[lo:lo + 4]) ** 2).mean().div(2).backward()
+        opt.step()
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.2)
+        ((ref(X) - Y) ** 2).mean().backward()
+        ropt.step()
+        res["accumulate"] = max((a - b).abs().max().item() for a, b in zip(model.parameters(), ref.parameters())) < 1e-6
+
+        # (2) clipping recipe: synchronize, clip the *averaged* gradients, step without a second reduction
+        model, ref = make(), make()
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.2), named_parameters=model.named_parameters())
+        opt.zero_grad()
+        ((model(X[8 * r:8 * r + 8]) - Y[8 * r:8 * r + 8]) ** 2).mean().backward()
+        opt.synchronize()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)
+        with opt.skip_synchronize():
+            opt.step()
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.2)
+        ((ref(X) - Y) ** 2).mean().backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+        ropt.step()
+        res["clip"] = max((a - b).abs().max().item() for a, b in zip(model.parameters(), ref.parameters())) < 1e-6
+
+        # (3) compression, in-place grouped allreduce
+        t = torch.full((6,), 1.0 + r)
+        c = hvd.allreduce(t, op=hvd.Sum, compression=hvd.Compression.fp16)
+        res["compression"] = c.dtype == torch.float32 and bool(torch.allclose(c, torch.full((6,), n * (n + 1) / 2.0)))
+        ts = [torch.full((k + 2,), float(r)) for k in range(3)]
+        outs = hvd.grouped_allreduce_(ts, op=hvd.Sum)
+        res["grouped_inplace"] = all(o is t_ and t_[0].item() == n * (n - 1) / 2.0 for o, t_ in zip(outs, ts))
+
+        # (4) autograd through collectives: d/dx of sum over ranks
+        x = torch.full((3,), float(r + 1), requires_grad=True)
+        hvd.allreduce(x * x, op=hvd.Sum).sum().backward()           # every rank differentiates the same global sum
+        res["d_allreduce"] = bool(torch.allclose(x.grad, 2 * x.detach() * n))
+        x = torch.full((r + 1, 2), 1.0, requires_grad=True)
+        g = hvd.allgather(x)
+        (g * torch.arange(g.shape[0], dtype=torch.float32).view(-1, 1)).sum().backward()
+        off = r * (r + 1) // 2
+        want = torch.arange(off, off + r + 1, dtype=torch.float32).view(-1, 1).expand(-1, 2) * n
+        res["d_allgather"] = bool(torch.allclose(x.grad, want))
+        x = torch.full((2,), float(r + 1), requires_grad=True)
+        (hvd.broadcast(x, root_rank=0) * (r + 1)).sum().backward()
+        res["d_broadcast"] = bool(torch.allclose(x.grad, torch.full((2,), n * (n + 1) / 2.0) if r == 0 else torch.zeros(2)))
+
+        # (5) refusals / stubs
+        try:
+            hvd.allreduce(torch.ones(2), op=hvd.Adasum)
+            res["adasum"] = False
+        except NotImplementedError:
+            res["adasum"] = True
+        res["global_set"] = hvd.add_process_set(list(range(n))) is hvd.global_process_set and hvd.global_process_set.size() == n
+        try:
+            hvd.add_process_set([0])
+            res["subset"] = n == 1
+        except NotImplementedError:
+            res["subset"] = True
+        return res
+    res = HorovodRunner(np=-2).run(main)
+    assert all(res.values()), res
