@@ -149,3 +149,38 @@ def test_no_orphan_processes_after_failure():
     after = [p for p in psutil.Process().children(recursive=True) if p.pid not in before and p.is_running()
              and p.status() != psutil.STATUS_ZOMBIE]
     assert not after, after
+
+
+def test_external_gang_under_torchrun(tmp_path):
+    """bench.py's multi-GPU launch mode: torchrun starts the ranks, every rank calls HorovodRunner.run with
+    SPARKDL_EXTERNAL_GANG=1 and joins the existing gang (store hosted by rank 0) instead of spawning workers."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "ext.py"
+    script.write_text(
+        "import os, sys, json\n"
+        "sys.path.insert(0, %r)\n"
+        "os.environ['SPARKDL_EXTERNAL_GANG'] = '1'\n"
+        "from sparkdl import HorovodRunner\n"
+        "def main(scale):\n"
+        "    import torch\n"
+        "    import sparkdl.hvd as hvd\n"
+        "    hvd.init()\n"
+        "    out = hvd.allreduce(torch.full((4,), float(hvd.rank() + 1)) * scale, op=hvd.Sum)\n"
+        "    objs = hvd.allgather_object({'r': hvd.rank()})\n"
+        "    res = (hvd.rank(), hvd.size(), out.tolist(), [o['r'] for o in objs])\n"
+        "    hvd.shutdown()\n"
+        "    return res\n"
+        "res = HorovodRunner(np=-2).run(main, scale=2.0)\n"
+        "open(os.path.join(%r, 'out.%%s.json' %% os.environ['RANK']), 'w').write(json.dumps(res))\n" % (root, str(tmp_path)))
+    port = 20000 + os.getpid() % 20000
+    env = dict(os.environ, SPARKDL_NUM_GPUS="0", CUDA_VISIBLE_DEVICES="", SPARKDL_FORCE_CPU="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    import json
+    for rank in (0, 1):
+        got = json.loads((tmp_path / ("out.%d.json" % rank)).read_text())
+        assert got == [rank, 2, [6.0] * 4, [0, 1]]
