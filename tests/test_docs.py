@@ -41,3 +41,16 @@ def test_generated_api_reference_is_complete():
     assert r.returncode == 0, r.stderr[-800:]
     text = open(os.path.join(ROOT, "docs", "API.md")).read()
     assert "(undocumented)" not in text and "HorovodRunner" in text and "allreduce" in text
+
+
+def test_every_environment_knob_is_documented():
+    """docs/CONFIG.md lists every SPARKDL_* variable the code reads."""
+    used = set()
+    for base in ("spark_deep_learning_b200", "sparkdl"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cc", ".cu", ".h", ".cuh")):
+                    used |= set(re.findall(r"SPARKDL_[A-Z0-9_]+", open(os.path.join(dirpath, f), errors="ignore").read()))
+    doc = open(os.path.join(ROOT, "docs", "CONFIG.md")).read()
+    missing = sorted(v for v in used if v not in doc and not v.endswith("_"))
+    assert not missing, missing
