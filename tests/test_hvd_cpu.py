@@ -416,3 +416,42 @@ def test_optimizer_recipes_and_differentiable_collectives():
         return res
     res = HorovodRunner(np=-2).run(main)
     assert all(res.values()), res
+
+
+def test_grad_views_survive_set_to_none_and_manual_grad_resets():
+    """SURVEY.md hard part 3: param.grad aliases the bucket; zero_grad(set_to_none=True), `p.grad = None` and a
+    replaced .grad tensor between steps must not break the averaging."""
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        r, n = hvd.rank(), hvd.size()
+        torch.manual_seed(3)
+        model = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.ReLU(), torch.nn.Linear(6, 1))
+        ref = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.ReLU(), torch.nn.Linear(6, 1))
+        ref.load_state_dict(model.state_dict())
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.5),
+                                       named_parameters=model.named_parameters(), bucket_bytes=64)
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.5)
+        gen = torch.Generator().manual_seed(5)
+        X, Y = torch.randn(6 * n, 4, generator=gen), torch.randn(6 * n, 1, generator=gen)
+        for step in range(4):
+            if step == 0:
+                opt.zero_grad(set_to_none=True)
+            elif step == 1:
+                opt.zero_grad()
+                for p in model.parameters():
+                    p.grad = None                                   # user code dropping the aliases
+            elif step == 2:
+                opt.zero_grad()
+                for p in model.parameters():
+                    p.grad = torch.zeros_like(p)                    # ... or replacing them by fresh tensors
+            else:
+                opt.zero_grad()
+            ((model(X[6 * r:6 * r + 6]) - Y[6 * r:6 * r + 6]) ** 2).mean().backward()
+            opt.step()
+            ropt.zero_grad()
+            ((ref(X) - Y) ** 2).mean().backward()
+            ropt.step()
+        return max((a - b).abs().max().item() for a, b in zip(model.parameters(), ref.parameters()))
+    assert HorovodRunner(np=-2).run(main) < 1e-6
