@@ -256,7 +256,7 @@ class _XgboostModel(Model, _XgboostParams, MLReadable, MLWritable):
         b = self._xgb_sklearn_model
         limit = gv("ntree_limit")
         if limit is None and b.best_iteration is not None:
-            limit = (b.best_iteration + 1) * b.n_groups
+            limit = (b.best_iteration + 1) * b.trees_per_round
         return b.predict_margin(Xt, bm, ntree_limit=limit).cpu()
 
     def _transform(self, dataset):

@@ -275,8 +275,13 @@ class Booster(object):
         return Booster.from_json(self.to_json())
 
     @property
+    def trees_per_round(self):
+        """Output groups x ``num_parallel_tree`` (a boosted random forest adds several trees per round)."""
+        return max(1, self.n_groups) * max(1, int(self.attributes.get("num_parallel_tree", 1)))
+
+    @property
     def num_boosted_rounds(self):
-        return len(self.trees) // max(1, self.num_class if self.objective.startswith("multi:") else 1)
+        return len(self.trees) // self.trees_per_round
 
     def get_dump(self):
         out = []
@@ -584,13 +589,13 @@ class _HistBuilder(object):
         return hist.view(n_nodes, self.F, MAX_BINS, 2)
 
 
-IGNORED_PARAMS = ("num_parallel_tree", "booster", "n_jobs", "importance_type", "tree_method")
+IGNORED_PARAMS = ("booster", "n_jobs", "importance_type", "tree_method")
 
 DEFAULTS = dict(scale_pos_weight=1.0, n_estimators=100, max_depth=6, learning_rate=0.3, gamma=0.0, min_child_weight=1.0, subsample=1.0,
                 colsample_bytree=1.0, reg_lambda=1.0, reg_alpha=0.0, max_bin=256, base_score=0.5, random_state=0,
                 objective=None, num_class=None, early_stopping_rounds=None, eval_metric=None, verbose=False,
                 max_delta_step=0.0, tree_method="hist", colsample_bylevel=1.0, colsample_bynode=1.0,
-                monotone_constraints=None, tweedie_variance_power=1.5, interaction_constraints=None)
+                monotone_constraints=None, tweedie_variance_power=1.5, interaction_constraints=None, num_parallel_tree=1)
 _ALIASES = {"eta": "learning_rate", "lambda": "reg_lambda", "alpha": "reg_alpha", "seed": "random_state",
             "min_split_loss": "gamma", "num_boost_round": "n_estimators", "verbosity": "verbose"}
 
@@ -739,6 +744,10 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
     def gain_of_weight(Gx, Hx, wx):                   # -2 * (G w + (H + lambda) w^2 / 2 + alpha |w|)
         return -(2.0 * Gx * wx + (Hx + lam) * wx * wx + 2.0 * alpha * wx.abs())
 
+    npt = max(1, int(p.get("num_parallel_tree") or 1))
+    if xgb_model is not None and int(booster.attributes.get("num_parallel_tree", 1)) != npt and booster.trees:
+        raise ValueError("xgb_model was trained with num_parallel_tree=%s" % booster.attributes.get("num_parallel_tree", 1))
+    booster.attributes["num_parallel_tree"] = npt
     sibling_subtract = os.environ.get("SPARKDL_GBDT_SIBLING_SUBTRACT", "1") != "0"
     skip_leaf_hist = os.environ.get("SPARKDL_GBDT_SKIP_LEAF_HIST", "1") != "0"
 
@@ -749,8 +758,10 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
             keep = (torch.rand(n, generator=rng) < float(p["subsample"])).to(device)
         else:
             keep = None
-        new_trees = []
-        for k in range(G):
+        new_trees, new_groups = [], []
+        for k, j in [(k_, j_) for k_ in range(G) for j_ in range(npt)]:
+            if j > 0 and float(p["subsample"]) < 1.0:        # every tree of a boosted forest draws its own rows
+                keep = (torch.rand(n, generator=rng) < float(p["subsample"])).to(device)
             g, h = g_all[:, k], h_all[:, k]
             # fixed-point quantisation: |q| <= 2^30 per row keeps int64 sums exact for < 2^32 rows
             gmax, hmax = dist.allreduce_host([float(g.abs().max()) if n else 0.0, float(h.abs().max()) if n else 0.0], "max")
@@ -803,7 +814,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                 hi_t = torch.tensor([node_hi[nid] for nid in level_nodes], device=device, dtype=torch.float64)
                 w_node = leaf_weight(Gt, Ht, lo_t, hi_t) if weighted_gain else leaf_weight(Gt, Ht)
                 for s, nid in enumerate(level_nodes):
-                    tree.value[nid] = float(w_node[s] * eta)
+                    tree.value[nid] = float(w_node[s] * eta / npt)
                     tree.cover[nid] = float(Ht[s])
                 if depth == max_depth:
                     break
@@ -949,13 +960,14 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                 delta = vals[node_of_row]
             margin[:, k] += delta
             new_trees.append(tree)
+            new_groups.append(k)
             booster.trees.append(tree)
             booster.tree_group.append(k)
         booster._packed = None
         rnd = start_round + it
         if ev is not None:
             tmp = Booster(objective, num_class, 0.0, missing, F)
-            tmp.trees, tmp.tree_group = new_trees, list(range(G))
+            tmp.trees, tmp.tree_group = new_trees, new_groups
             ev["margin"] += tmp.predict_margin(ev["X"], zero_base=True)
             scores = {}
             for m in metrics:

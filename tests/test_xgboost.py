@@ -166,7 +166,7 @@ def test_scale_pos_weight_and_ignored_param_warning():
     rec = lambda o: ((o["prediction"].to_numpy() == 1) & (yb == 1)).sum() / max(1, (yb == 1).sum())  # noqa: E731
     assert rec(heavy) >= rec(plain)
     with pytest.warns(UserWarning, match="not used by the B200 GBDT engine"):
-        XgboostRegressor(n_estimators=2, num_parallel_tree=4).fit(pd.DataFrame({"features": list(X), "label": y}))
+        XgboostRegressor(n_estimators=2, booster="dart").fit(pd.DataFrame({"features": list(X), "label": y}))
 
 
 def _three_class_frame(n=900, seed=3):
@@ -397,3 +397,28 @@ def test_distributed_auc_early_stopping_is_consistent(monkeypatch):
     assert bd.num_boosted_rounds < 60                                  # it did stop early
     assert bs.best_iteration == bd.best_iteration and abs(bs.best_score - bd.best_score) < 1e-6
     assert np.allclose(single._evals_result["validation_0"]["auc"], dist._evals_result["validation_0"]["auc"], atol=1e-6)
+
+
+def test_num_parallel_tree_boosted_forest(tmp_path):
+    """num_parallel_tree: several trees per round on their own row samples, leaf values scaled by 1/k; rounds,
+    early-stopping limits and persistence count trees_per_round."""
+    from spark_deep_learning_b200.xgboost import gbdt
+    rng = np.random.RandomState(0)
+    X = rng.rand(2500, 6).astype(np.float32)
+    y = (np.sin(6 * X[:, 0]) + X[:, 1] * X[:, 2] + 0.3 * rng.randn(2500)).astype(np.float32)
+    Xt = rng.rand(1500, 6).astype(np.float32)
+    yt = np.sin(6 * Xt[:, 0]) + Xt[:, 1] * Xt[:, 2]
+    one, _ = gbdt.train(dict(n_estimators=1, learning_rate=1.0, max_depth=6), X, y)
+    forest, _ = gbdt.train(dict(n_estimators=1, learning_rate=1.0, max_depth=6, num_parallel_tree=20, subsample=0.6,
+                                colsample_bynode=0.7), X, y)
+    rmse = lambda b: float(np.sqrt(np.mean((np.asarray(b.predict(Xt)).ravel() - yt) ** 2)))  # noqa: E731
+    assert len(forest.trees) == 20 and forest.num_boosted_rounds == 1 and rmse(forest) < rmse(one)
+    df = pd.DataFrame({"features": list(X), "label": y, "isVal": rng.rand(2500) < 0.25})
+    m = XgboostRegressor(n_estimators=30, num_parallel_tree=3, subsample=0.7, max_depth=3, early_stopping_rounds=2,
+                         validationIndicatorCol="isVal", learning_rate=0.8).fit(df)
+    b = m.get_booster()
+    assert len(b.trees) == 3 * b.num_boosted_rounds and b.trees_per_round == 3
+    m.write().overwrite().save(str(tmp_path / "rf"))
+    again = XgboostRegressorModel.load(str(tmp_path / "rf"))
+    assert again.get_booster().trees_per_round == 3
+    assert np.allclose(again.transform(df)["prediction"], m.transform(df)["prediction"])
