@@ -813,9 +813,10 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
                 lo_t = torch.tensor([node_lo[nid] for nid in level_nodes], device=device, dtype=torch.float64)
                 hi_t = torch.tensor([node_hi[nid] for nid in level_nodes], device=device, dtype=torch.float64)
                 w_node = leaf_weight(Gt, Ht, lo_t, hi_t) if weighted_gain else leaf_weight(Gt, Ht)
+                vals_l, cover_l = (w_node * eta / npt).tolist(), Ht.tolist()      # one device->host copy per level
                 for s, nid in enumerate(level_nodes):
-                    tree.value[nid] = float(w_node[s] * eta / npt)
-                    tree.cover[nid] = float(Ht[s])
+                    tree.value[nid] = vals_l[s]
+                    tree.cover[nid] = cover_l[s]
                 if depth == max_depth:
                     break
                 hist = hist_int.to(torch.float64)
