@@ -455,3 +455,30 @@ def test_grad_views_survive_set_to_none_and_manual_grad_resets():
             ropt.step()
         return max((a - b).abs().max().item() for a, b in zip(model.parameters(), ref.parameters()))
     assert HorovodRunner(np=-2).run(main) < 1e-6
+
+
+def test_sparse_embedding_gradients_are_reduced_as_dense():
+    """nn.Embedding(sparse=True) under DistributedOptimizer (Horovod's sparse_as_dense): the sparse gradient lands in the
+    dense bucket view and is averaged like any other."""
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        r, n = hvd.rank(), hvd.size()
+        torch.manual_seed(0)
+        emb = torch.nn.Embedding(20, 4, sparse=True)
+        ref = torch.nn.Embedding(20, 4)
+        ref.load_state_dict(emb.state_dict())
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(emb.parameters(), lr=0.5), named_parameters=emb.named_parameters(),
+                                       sparse_as_dense=True)
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.5)
+        idx = torch.tensor([[1, 2, 3], [4, 5, 6], [7, 8, 9], [1, 5, 9]])
+        for _ in range(3):
+            opt.zero_grad()
+            emb(idx[r]).pow(2).sum().backward()
+            opt.step()
+            ropt.zero_grad()
+            (sum(ref(idx[q]).pow(2).sum() for q in range(n)) / n).backward()
+            ropt.step()
+        return (emb.weight - ref.weight).abs().max().item()
+    assert HorovodRunner(np=-2).run(main) < 1e-6
