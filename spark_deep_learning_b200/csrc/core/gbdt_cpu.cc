@@ -36,7 +36,9 @@ extern "C" {
 // n_nodes * F * 256 * 2 int64; pos values must lie in [-1, n_nodes).
 int sdl_gbdt_hist_cpu(const uint8_t* bins, const int32_t* gh, const int32_t* pos, int64_t* hist, int64_t n, int F,
                       int n_nodes, int max_threads) {
-  if (!bins || !gh || !pos || !hist || n < 0 || F <= 0 || n_nodes <= 0) return -1;
+  if (!hist || n < 0 || F <= 0 || n_nodes <= 0) return -1;
+  if (n == 0) return 0;                            // an empty shard (its tensors have null data pointers)
+  if (!bins || !gh || !pos) return -1;
   for (int64_t r = 0; r < n; ++r)
     if (pos[r] >= n_nodes) return -1;
   int hw = (int)std::thread::hardware_concurrency();

@@ -107,3 +107,31 @@ def test_native_cpu_histogram_matches_numpy():
     assert torch.equal(one, hist)
     pos[17] = nodes
     assert lib.sdl_gbdt_hist_cpu(bins.data_ptr(), gh.data_ptr(), pos.data_ptr(), one.data_ptr(), n, F, nodes, 0) == -1
+
+
+def test_native_cpu_histogram_property():
+    """Random shapes (including empty shards, one feature, every row inactive): always equal to the numpy scatter-add."""
+    import numpy as np
+    import torch
+    from hypothesis import given, settings, strategies as st
+    from spark_deep_learning_b200.parallel import core
+    lib = core.load()
+
+    @settings(max_examples=25, deadline=None)
+    @given(n=st.integers(0, 3000), F=st.integers(1, 9), nodes=st.integers(1, 6), seed=st.integers(0, 10 ** 6),
+           threads=st.integers(0, 4))
+    def check(n, F, nodes, seed, threads):
+        rng = np.random.RandomState(seed)
+        bins = torch.from_numpy(rng.randint(0, 256, size=(n, F)).astype(np.uint8))
+        gh = torch.from_numpy(rng.randint(-2 ** 30, 2 ** 30, size=(n, 2)).astype(np.int32))
+        pos = torch.from_numpy(rng.randint(-1, nodes, size=n).astype(np.int32))
+        hist = torch.zeros(nodes * F * 256 * 2, dtype=torch.int64)
+        assert lib.sdl_gbdt_hist_cpu(bins.data_ptr(), gh.data_ptr(), pos.data_ptr(), hist.data_ptr(), n, F, nodes, threads) == 0
+        ref = np.zeros((nodes, F, 256, 2), dtype=np.int64)
+        act = pos.numpy() >= 0
+        p, b, q = pos.numpy()[act], bins.numpy()[act], gh.numpy()[act].astype(np.int64)
+        for f in range(F):
+            np.add.at(ref[:, f, :, 0], (p, b[:, f]), q[:, 0])
+            np.add.at(ref[:, f, :, 1], (p, b[:, f]), q[:, 1])
+        assert np.array_equal(hist.numpy().reshape(ref.shape), ref)
+    check()
