@@ -422,3 +422,66 @@ def test_num_parallel_tree_boosted_forest(tmp_path):
     again = XgboostRegressorModel.load(str(tmp_path / "rf"))
     assert again.get_booster().trees_per_round == 3
     assert np.allclose(again.transform(df)["prediction"], m.transform(df)["prediction"])
+
+
+def test_gbdt_fuzz_three_workers_equal_single_worker(monkeypatch):
+    """Ten seeded random configurations (objective, depth, regularisation, column sampling, coarse max_bin, monotone /
+    interaction constraints, weights, NaN or 0.0 as missing): 3 row-sharded workers build the single-worker trees."""
+    import random
+    from sparkdl import HorovodRunner
+    from spark_deep_learning_b200.xgboost import gbdt
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "0")
+    rnd = random.Random(5)
+    cfgs = []
+    for _ in range(10):
+        obj = rnd.choice(["reg:squarederror", "binary:logistic", "multi:softprob", "count:poisson", "reg:pseudohubererror"])
+        p = dict(objective=obj, n_estimators=rnd.randint(2, 4), max_depth=rnd.randint(1, 5), learning_rate=rnd.choice([0.1, 0.3, 1.0]),
+                 reg_lambda=rnd.choice([0.0, 1.0, 5.0]), reg_alpha=rnd.choice([0.0, 0.5]), gamma=rnd.choice([0.0, 0.1]),
+                 min_child_weight=rnd.choice([0.0, 1.0, 5.0]), colsample_bytree=rnd.choice([1.0, 0.6]),
+                 colsample_bynode=rnd.choice([1.0, 0.7]), max_bin=rnd.choice([256, 16, 4]), max_delta_step=rnd.choice([0.0, 0.5]),
+                 random_state=rnd.randint(0, 99))
+        if rnd.random() < 0.3:
+            p["monotone_constraints"] = [rnd.choice([-1, 0, 1]) for _ in range(5)]
+        if rnd.random() < 0.3:
+            p["interaction_constraints"] = [[0, 1], [2, 3, 4]]
+        if obj == "multi:softprob":
+            p["num_class"] = 3
+        cfgs.append((p, rnd.randint(0, 10 ** 6), rnd.choice([float("nan"), 0.0])))
+
+    def make(p, dseed, missing):
+        import numpy as np
+        rng = np.random.RandomState(dseed)
+        n = rng.randint(50, 500)
+        X = rng.randn(n, 5).astype(np.float32)
+        X[rng.rand(n, 5) < 0.15] = missing
+        base = np.nan_to_num(X[:, 0]) - np.nan_to_num(X[:, 1]) * np.nan_to_num(X[:, 2])
+        obj = p["objective"]
+        if obj == "binary:logistic":
+            y = (base > 0).astype(np.float32)
+        elif obj == "multi:softprob":
+            y = np.digitize(base, [-0.5, 0.5]).astype(np.float32)
+        elif obj == "count:poisson":
+            y = rng.poisson(np.exp(np.clip(base, -2, 2))).astype(np.float32)
+        else:
+            y = (base + 0.1 * rng.randn(n)).astype(np.float32)
+        return X, y, rng.uniform(0.5, 2.0, n).astype(np.float32)
+
+    def worker(cfgs):
+        import numpy as np
+        import sparkdl.hvd as hvd
+        from spark_deep_learning_b200.xgboost import gbdt as g
+        hvd.init()
+        outs = []
+        for p, dseed, missing in cfgs:
+            X, y, w = make(p, dseed, missing)
+            idx = np.array_split(np.arange(len(y)), hvd.size())[hvd.rank()]
+            outs.append(g.train(p, X[idx], y[idx], weight=w[idx], missing=missing)[0].to_json())
+        return outs
+    dist = HorovodRunner(np=-3).run(worker, cfgs=cfgs)
+    for (p, dseed, missing), jd in zip(cfgs, dist):
+        X, y, w = make(p, dseed, missing)
+        bs = gbdt.train(p, X, y, weight=w, missing=missing)[0]
+        bd = gbdt.Booster.from_json(jd)
+        assert [t.feature for t in bs.trees] == [t.feature for t in bd.trees], p
+        ps, pd_ = np.asarray(bs.predict(X, output_margin=True)), np.asarray(bd.predict(X, output_margin=True))
+        assert np.abs(ps - pd_).max() < 1e-4, p
