@@ -485,3 +485,26 @@ def test_gbdt_fuzz_three_workers_equal_single_worker(monkeypatch):
         assert [t.feature for t in bs.trees] == [t.feature for t in bd.trees], p
         ps, pd_ = np.asarray(bs.predict(X, output_margin=True)), np.asarray(bd.predict(X, output_margin=True))
         assert np.abs(ps - pd_).max() < 1e-4, p
+
+
+def test_accuracy_is_on_par_with_sklearn_hist_gradient_boosting():
+    """Independent reference (xgboost itself is not installable offline): same depth / rounds / learning rate / L2 as
+    scikit-learn's histogram GBDT must give comparable held-out error on regression and classification."""
+    from sklearn.ensemble import HistGradientBoostingClassifier, HistGradientBoostingRegressor
+    from spark_deep_learning_b200.xgboost import gbdt
+    f = lambda X: 2 * np.sin(X[:, 0]) + X[:, 1] * X[:, 2] + (X[:, 3] > 0.5) * 1.5 + 0.5 * X[:, 4] ** 2  # noqa: E731
+    rng = np.random.RandomState(2)
+    X, Xt = rng.randn(4000, 8).astype(np.float32), rng.randn(2000, 8).astype(np.float32)
+    y = (f(X) + 0.3 * rng.randn(4000)).astype(np.float32)
+    common = dict(max_leaf_nodes=None, min_samples_leaf=1, l2_regularization=1.0, early_stopping=False)
+    sk = HistGradientBoostingRegressor(max_iter=60, learning_rate=0.1, max_depth=5, **common).fit(X, y)
+    us, _ = gbdt.train(dict(n_estimators=60, learning_rate=0.1, max_depth=5), X, y)
+    r_sk = np.sqrt(np.mean((sk.predict(Xt) - f(Xt)) ** 2))
+    r_us = np.sqrt(np.mean((np.asarray(us.predict(Xt)).ravel() - f(Xt)) ** 2))
+    assert r_us < 1.15 * r_sk, (r_us, r_sk)
+    yb = (f(X) + 0.5 * rng.randn(4000) > 1.0).astype(np.float32)
+    skc = HistGradientBoostingClassifier(max_iter=40, learning_rate=0.2, max_depth=4, **common).fit(X, yb)
+    usc, _ = gbdt.train(dict(objective="binary:logistic", n_estimators=40, learning_rate=0.2, max_depth=4), X, yb)
+    a_sk = (skc.predict(Xt) == (f(Xt) > 1.0)).mean()
+    a_us = ((np.asarray(usc.predict(Xt)).ravel() > 0.5) == (f(Xt) > 1.0)).mean()
+    assert a_us > a_sk - 0.02, (a_us, a_sk)
