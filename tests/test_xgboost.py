@@ -508,3 +508,35 @@ def test_accuracy_is_on_par_with_sklearn_hist_gradient_boosting():
     a_sk = (skc.predict(Xt) == (f(Xt) > 1.0)).mean()
     a_us = ((np.asarray(usc.predict(Xt)).ravel() > 0.5) == (f(Xt) > 1.0)).mean()
     assert a_us > a_sk - 0.02, (a_us, a_sk)
+
+
+def test_spark_dataframe_adapter_with_a_duck_typed_frame():
+    """pyspark is not installable here: exercise the Spark branch of the dataset adapter (toPandas in, createDataFrame
+    out, vector objects with .toArray()) with a stand-in that has exactly that interface."""
+    class Vec(object):
+        def __init__(self, values):
+            self._v = np.asarray(values, dtype=np.float64)
+
+        def toArray(self):
+            return self._v
+
+    class Session(object):
+        def createDataFrame(self, pdf):
+            return FakeSparkFrame(pdf)
+
+    class FakeSparkFrame(object):
+        sparkSession = Session()
+
+        def __init__(self, pdf):
+            self._pdf = pdf
+
+        def toPandas(self):
+            return self._pdf.copy()
+    X, y = _toy(400, f=5)
+    sdf = FakeSparkFrame(pd.DataFrame({"features": [Vec(r) for r in X], "label": y}))
+    model = XgboostRegressor(n_estimators=10, max_depth=3).fit(sdf)
+    out = model.transform(sdf)
+    assert isinstance(out, FakeSparkFrame)
+    pdf = out.toPandas()
+    ref = XgboostRegressor(n_estimators=10, max_depth=3).fit(pd.DataFrame({"features": list(X), "label": y}))
+    assert np.allclose(pdf["prediction"], ref.transform(pd.DataFrame({"features": list(X)}))["prediction"])
