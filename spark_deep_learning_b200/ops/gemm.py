@@ -7,6 +7,7 @@ library GEMMs (cuBLAS through torch.matmul) for dgrad / wgrad plus the analytic 
 the saved pre-activation.
 """
 import ctypes
+import os
 
 import torch
 
@@ -15,6 +16,8 @@ from spark_deep_learning_b200.utils import launch_counter
 
 ACT = {None: 0, "none": 0, "gelu_tanh": 1, "gelu": 2, "gelu_erf": 2}
 _sig = False
+# EXPERIMENTAL: 16-epilogue-warp kernel variant (gemm_tcgen05_epi16.cu), opt-in until it has been run on hardware
+_EPI16 = os.environ.get("SPARKDL_GEMM_EPI16", "0") == "1"
 
 
 def _lib():
@@ -26,6 +29,9 @@ def _lib():
         lib.sdlc_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, u64]
         lib.sdlc_gelu_bwd.restype = i32
         lib.sdlc_gelu_bwd.argtypes = [vp, vp, vp, ctypes.c_longlong, i32, u64]
+        if _EPI16:
+            lib.sdlc_gemm_bf16_epi16.restype = i32
+            lib.sdlc_gemm_bf16_epi16.argtypes = lib.sdlc_gemm_bf16.argtypes
         _sig = True
     return lib
 
@@ -54,8 +60,9 @@ def gemm_bf16(x2d, weight, bias=None, act=None, save_pre_act=False, block_n=None
     if block_n is None:
         # enough tiles to fill 148 SMs with the wide tile? otherwise use the narrow one
         block_n = 256 if ((m + 127) // 128) * ((n + 255) // 256) >= 148 else 128
-    rc = lib.sdlc_gemm_bf16(_p(x2d), _p(weight), _p(bias), _p(out), _p(pre), m, n, k, ACT[act], block_n, 0,
-                            torch.cuda.current_stream(x2d.device).cuda_stream)
+    fn = lib.sdlc_gemm_bf16_epi16 if _EPI16 else lib.sdlc_gemm_bf16
+    rc = fn(_p(x2d), _p(weight), _p(bias), _p(out), _p(pre), m, n, k, ACT[act], block_n, 0,
+            torch.cuda.current_stream(x2d.device).cuda_stream)
     if rc != 0:
         raise RuntimeError("sdlc_gemm_bf16 failed (%d) for M=%d N=%d K=%d" % (rc, m, n, k))
     launch_counter.add(1)
