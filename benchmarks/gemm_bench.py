@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""tcgen05 GEMM vs cuBLAS (torch) on the BERT-large forward shapes and one large square-ish shape.
+"""tcgen05 GEMM (``ops/gemm.py``) vs cuBLAS (torch.matmul) on the BERT-large shapes, forward AND backward.
 
-    python benchmarks/gemm_bench.py                     # default kernel
-    SPARKDL_GEMM_EPI16=1 python benchmarks/gemm_bench.py # experimental 16-epilogue-warp variant
+    python benchmarks/gemm_bench.py [--quick]
 
-CUDA-event timing, L2 flushed between iterations (256 MB memset), numerics checked against an fp32 reference first.
-Writes gpurun_out/gemm_bench[_epi16].json.
+For every (M, N, K) the three GEMMs of a linear layer are timed: forward ``X.W^T`` (+bias / +GELU), dgrad ``dY.W`` and
+wgrad ``dY^T.X`` (the same FLOPs each).  CUDA events, median of 20, L2 flushed between iterations (256 MB memset).
+The cuBLAS arm is what torch dispatches for the same math (``F.linear`` / ``@`` on the same, untransposed tensors).
+Writes gpurun_out/gemm_bench.json.
 """
 import json
 import os
@@ -16,9 +17,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-SHAPES = [  # (M, N, K, act)
-    (8192, 3072, 1024, None), (8192, 1024, 1024, None), (8192, 4096, 1024, "gelu"), (8192, 1024, 4096, None),
-    (8192, 30528, 1024, None), (8192, 4096, 4096, None), (8192, 4096, 4096, "gelu"),
+SHAPES = [  # (M = tokens, N = out features, K = in features)
+    (4096, 1024, 1024), (4096, 4096, 1024), (4096, 1024, 4096), (4096, 30528, 1024), (8192, 4096, 4096),
+    (8192, 1024, 1024), (8192, 4096, 1024), (8192, 1024, 4096), (8192, 3072, 1024),
 ]
 
 
@@ -41,24 +42,33 @@ def main():
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
-    for m, n, k, act in SHAPES:
+    shapes = SHAPES[:3] if "--quick" in sys.argv else SHAPES
+    for m, n, k in shapes:
         x = torch.randn(m, k, device=dev, dtype=torch.bfloat16)
         w = torch.randn(n, k, device=dev, dtype=torch.bfloat16) * 0.05
         b = torch.randn(n, device=dev, dtype=torch.float32)
-        ref = F.linear(x[:256].float(), w.float(), b)
-        ref = F.gelu(ref) if act else ref
-        out, _ = gemm.gemm_bf16(x, w, b, act, save_pre_act=bool(act))
-        err = (out[:256].float() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
-        t_ours = timeit(lambda: gemm.gemm_bf16(x, w, b, act, save_pre_act=bool(act)), flush)
         wb = b.to(torch.bfloat16)
-        t_lib = timeit(lambda: F.gelu(F.linear(x, w, wb)) if act else F.linear(x, w, wb), flush)
+        dy = torch.randn(m, n, device=dev, dtype=torch.bfloat16)
+        pre = torch.randn(m, k, device=dev, dtype=torch.bfloat16)
         fl = 2.0 * m * n * k
-        rows.append({"M": m, "N": n, "K": k, "act": act or "none", "rel_err": err, "ours_us": t_ours, "lib_us": t_lib,
-                     "ours_tflops": fl / t_ours / 1e6, "lib_tflops": fl / t_lib / 1e6})
-        print(rows[-1], flush=True)
-    tag = "_epi16" if os.environ.get("SPARKDL_GEMM_EPI16") == "1" else ""
+        cases = [
+            ("fwd+bias", lambda: gemm.gemm_bf16(x, w, b, None), lambda: F.linear(x, w, wb)),
+            ("fwd+bias+gelu", lambda: gemm.gemm_bf16(x, w, b, "gelu", save_pre_act=True), lambda: F.gelu(F.linear(x, w, wb))),
+            ("dgrad", lambda: gemm.dgrad(dy, w), lambda: dy @ w),
+            ("dgrad*dgelu", lambda: gemm.dgrad(dy, w, pre, "gelu"), None),
+            ("wgrad", lambda: gemm.wgrad(dy, x), lambda: dy.t() @ x),
+        ]
+        for name, ours, lib in cases:
+            if n > 8192 and name in ("fwd+bias+gelu", "dgrad*dgelu"):
+                continue
+            t_ours = timeit(ours, flush)
+            t_lib = timeit(lib, flush) if lib is not None else float("nan")
+            rows.append({"M": m, "N": n, "K": k, "op": name, "ours_us": round(t_ours, 2), "lib_us": round(t_lib, 2),
+                         "ours_tflops": round(fl / t_ours / 1e6, 1), "lib_tflops": round(fl / t_lib / 1e6, 1),
+                         "ours_over_lib": round(t_lib / t_ours, 3)})
+            print(rows[-1], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "gemm_bench%s.json" % tag), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "gemm_bench.json"), "w") as f:
         json.dump(rows, f, indent=1)
 
 

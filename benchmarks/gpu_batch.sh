@@ -1,0 +1,32 @@
+#!/bin/bash
+# Parameterised GPU batch (replaces the one-shot gpu_callNN.sh scripts of round 1): every stage writes its own log
+# under gpurun_out/ and runs under its own timeout.
+#   gpurun --timeout 1500 -- 'bash benchmarks/gpu_batch.sh gemm pytest bench'
+#   gpurun --gpus 2 --timeout 1500 -- 'bash benchmarks/gpu_batch.sh multi2 sweep2'
+mkdir -p gpurun_out
+for stage in "$@"; do
+  echo "=== stage $stage ($(date +%T))"
+  case "$stage" in
+    gemm)      for g in fwd bwd wgrad stats autograd; do
+                 (timeout 150 python benchmarks/gemm_check.py $g 2>&1 | tail -80) > gpurun_out/gemm_check_$g.txt
+                 echo "gemm_check $g: $(tail -1 gpurun_out/gemm_check_$g.txt) ($(grep -c '^BAD' gpurun_out/gemm_check_$g.txt) bad)"
+               done ;;
+    gemmbench) (timeout 400 python benchmarks/gemm_bench.py 2>&1 | tail -60) > gpurun_out/gemm_bench.txt; tail -50 gpurun_out/gemm_bench.txt ;;
+    gemmquick) (timeout 200 python benchmarks/gemm_bench.py --quick 2>&1 | tail -30) > gpurun_out/gemm_bench_quick.txt; cat gpurun_out/gemm_bench_quick.txt ;;
+    pytest)    (timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) > gpurun_out/pytest_gpu.txt; tail -6 gpurun_out/pytest_gpu.txt ;;
+    pytestall) (timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40) > gpurun_out/pytest_gpu.txt; tail -30 gpurun_out/pytest_gpu.txt ;;
+    multi)     (timeout 900 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -25) > gpurun_out/pytest_multi.txt; tail -12 gpurun_out/pytest_multi.txt ;;
+    bench)     (timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 2> gpurun_out/bench1.err | tail -1) > gpurun_out/bench1.json; cat gpurun_out/bench1.json ;;
+    benchbert) (timeout 300 python bench.py --model bert-large --gpus 1 --steps 20 --warmup 5 2> gpurun_out/bert1.err | tail -1) > gpurun_out/bert1.json; cat gpurun_out/bert1.json ;;
+    benchref)  (timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 2> gpurun_out/ref1.err | tail -1) > gpurun_out/ref1.json; cat gpurun_out/ref1.json ;;
+    bertref)   (timeout 300 python bench.py --impl reference --model bert-large --gpus 1 --steps 20 --warmup 5 2> gpurun_out/bertref1.err | tail -1) > gpurun_out/bertref1.json; cat gpurun_out/bertref1.json ;;
+    fuzz1)     (timeout 300 python benchmarks/fuzz_collectives.py --np 1 --cases 200 2>&1 | tail -3) > gpurun_out/fuzz_np1.txt; cat gpurun_out/fuzz_np1.txt ;;
+    fuzz2)     (timeout 400 python benchmarks/fuzz_collectives.py --np 2 --cases 300 2>&1 | tail -3) > gpurun_out/fuzz_np2.txt; cat gpurun_out/fuzz_np2.txt ;;
+    fuzz8)     (timeout 400 python benchmarks/fuzz_collectives.py --np 8 --cases 150 2>&1 | tail -3) > gpurun_out/fuzz_np8.txt; cat gpurun_out/fuzz_np8.txt ;;
+    probes)    (timeout 300 python benchmarks/resnet_probe.py 2>&1 | tail -30) > gpurun_out/resnet_probe.txt
+               (timeout 300 python benchmarks/bert_probe.py 2>&1 | tail -30) > gpurun_out/bert_probe.txt
+               tail -12 gpurun_out/resnet_probe.txt gpurun_out/bert_probe.txt ;;
+    xgb)       (timeout 400 python benchmarks/xgboost_bench.py --np 1 2>&1 | tail -8) > gpurun_out/xgb_np1.txt; cat gpurun_out/xgb_np1.txt ;;
+    *)         echo "unknown stage $stage" ;;
+  esac
+done

@@ -1,7 +1,11 @@
 // C ABI of libsparkdl_core.so, consumed from Python through ctypes
 // (spark_deep_learning_b200/parallel/core.py).
+#include <unistd.h>
+
+#include <chrono>
 #include <cstring>
 #include <string>
+#include <thread>
 
 #include "engine.h"
 
@@ -119,5 +123,15 @@ void sdl_reduce_into(void* dst, const void* src, int64_t n, uint32_t dtype, uint
   reduce_into(dst, src, n, dtype, op);
 }
 void sdl_scale_buffer(void* buf, int64_t n, uint32_t dtype, double f) { scale_buffer(buf, n, dtype, f); }
+
+// Last-resort exit watchdog for worker processes: the worker leaves through the normal interpreter shutdown
+// (so at-exit hooks run), and this detached native thread ends the process with `code` if the shutdown has not
+// completed after `seconds` (a wedged CUDA context teardown must not hold the whole gang).
+void sdl_exit_watchdog(double seconds, int code) {
+  std::thread([seconds, code]() {
+    std::this_thread::sleep_for(std::chrono::duration<double>(seconds));
+    _exit(code);
+  }).detach();
+}
 
 }  // extern "C"

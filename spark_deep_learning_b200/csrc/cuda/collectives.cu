@@ -607,7 +607,7 @@ int sdlc_allreduce_wire(void* h, int channel, void* storage, long long numel, in
   }
   const long long units = ceil_div_ll(numel, kUnit);
   // phases 0 and 2 are local HBM passes over the whole tensor: use up to kMaxBlocks CTAs, not just comm_ctas
-  long long want = ceil_div_ll(units / (c->world > 0 ? 1 : 1), (kThreads / 16) * 4);
+  long long want = ceil_div_ll(units, (kThreads / 16) * 4);
   if (want < 1) want = 1;
   const int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : want);
   if (dtype == kF32) {

@@ -90,15 +90,31 @@ CollCtx Comm::make_ctx(int channel, int buf, size_t offset) const {
   return c;
 }
 
-cudaEvent_t Comm::next_event() {
+cudaEvent_t Comm::acquire_event(int refs) {
   std::lock_guard<std::mutex> g(mu);
-  if (event_pool.empty()) {
-    event_pool.resize(512);
-    for (auto& e : event_pool) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  cudaEvent_t e = nullptr;
+  if (!free_events.empty()) {
+    e = free_events.back();
+    free_events.pop_back();
+  } else {
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    all_events.push_back(e);
   }
-  cudaEvent_t e = event_pool[event_next % event_pool.size()];
-  ++event_next;
+  event_refs[e] = refs < 1 ? 1 : refs;
   return e;
+}
+
+void Comm::release_event(cudaEvent_t e) {
+  if (!e) return;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = event_refs.find(e);
+  if (it == event_refs.end()) return;   // not ours, or already back on the free list
+  if (--it->second > 0) return;
+  event_refs.erase(it);
+  free_events.push_back(e);
 }
 
 static size_t round_up(size_t x, size_t g) { return (x + g - 1) / g * g; }
@@ -147,7 +163,7 @@ void sdlc_comm_destroy(void* h) {
   cudaDeviceSynchronize();
   for (auto& s : c->streams)
     if (s) cudaStreamDestroy(s);
-  for (auto& e : c->event_pool) cudaEventDestroy(e);
+  for (auto& e : c->all_events) cudaEventDestroy(e);
   for (auto& e : c->table_events)
     if (e) cudaEventDestroy(e);
   if (c->epoch) cudaFree(c->epoch);
@@ -394,13 +410,26 @@ unsigned long long sdlc_channel_stream(void* h, int ch) {
 
 unsigned long long sdlc_record_event(void* h, unsigned long long stream) {
   Comm* c = static_cast<Comm*>(h);
-  cudaEvent_t e = c->next_event();
-  if (cudaEventRecord(e, reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess) {
+  cudaEvent_t e = c->acquire_event();
+  if (!e || cudaEventRecord(e, reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess) {
     c->last_error = "cudaEventRecord failed";
     cudaGetLastError();
+    c->release_event(e);
     return 0;
   }
   return reinterpret_cast<unsigned long long>(e);
+}
+
+// Give an event from sdlc_record_event / the engine executor back to the pool.  Legal as soon as every
+// cudaStreamWaitEvent / cudaEventSynchronize that needs it has been *issued* (a wait binds to the record that
+// preceded it, so a later re-record cannot disturb it).
+void sdlc_release_event(void* h, unsigned long long event) {
+  static_cast<Comm*>(h)->release_event(reinterpret_cast<cudaEvent_t>(event));
+}
+unsigned long long sdlc_event_pool_size(void* h) {
+  Comm* c = static_cast<Comm*>(h);
+  std::lock_guard<std::mutex> g(c->mu);
+  return c->all_events.size();
 }
 
 int sdlc_stream_wait_event(unsigned long long stream, unsigned long long event) {

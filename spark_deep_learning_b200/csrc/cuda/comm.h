@@ -10,6 +10,7 @@
 
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "sdl_cuda.cuh"
@@ -43,8 +44,11 @@ struct Comm {
   size_t oneshot_max_bytes = 512 << 10;
   bool use_mc = true;
   std::mutex mu;
-  std::vector<cudaEvent_t> event_pool;
-  size_t event_next = 0;
+  // Owned events: an event handed out by acquire_event() is never re-recorded until every holder has
+  // released it (a round-robin ring could wrap onto an event that a pending cudaStreamWaitEvent still needs).
+  std::vector<cudaEvent_t> all_events;
+  std::vector<cudaEvent_t> free_events;
+  std::unordered_map<cudaEvent_t, int> event_refs;
   // pinned pointer-table ring for batched pack/unpack
   void* table_host = nullptr;
   void* table_dev = nullptr;
@@ -54,7 +58,8 @@ struct Comm {
   unsigned long long launches = 0;        // kernels launched by this communicator
 
   CollCtx make_ctx(int channel, int buf, size_t offset) const;
-  cudaEvent_t next_event();
+  cudaEvent_t acquire_event(int refs = 1);
+  void release_event(cudaEvent_t e);
 };
 
 const char* cu_error_name(CUresult r);

@@ -228,7 +228,11 @@ extern "C" int sdlc_engine_exec(void* ctx, const sdl::GpuWork* w, uint64_t* done
   cudaStream_t stream = c->streams[0];
   const unsigned long long s = reinterpret_cast<unsigned long long>(stream);
   for (uint32_t i = 0; i < w->n; ++i)
-    if (w->ready_events[i]) cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(w->ready_events[i]), 0);
+    if (w->ready_events[i]) {
+      cudaEvent_t re = reinterpret_cast<cudaEvent_t>(w->ready_events[i]);
+      cudaStreamWaitEvent(stream, re, 0);
+      c->release_event(re);   // the wait is issued: the producer-side event can be recycled
+    }
   Fail fail{err, errlen};
   int rc;
   switch (w->type) {
@@ -240,8 +244,9 @@ extern "C" int sdlc_engine_exec(void* ctx, const sdl::GpuWork* w, uint64_t* done
     default: snprintf(err, errlen, "unsupported CUDA collective type %u", w->type); rc = -1;
   }
   if (rc != 0) return rc;
-  cudaEvent_t ev = c->next_event();
-  if (cudaEventRecord(ev, stream) != cudaSuccess) {
+  // one completion event shared by the w->n tensors of this (fused) response; each handle releases it once
+  cudaEvent_t ev = c->acquire_event((int)w->n);
+  if (!ev || cudaEventRecord(ev, stream) != cudaSuccess) {
     snprintf(err, errlen, "cudaEventRecord failed: %s", cudaGetErrorString(cudaGetLastError()));
     return -1;
   }

@@ -78,6 +78,8 @@ def load():
         "sdlc_record_event": (u64, [vp, u64]),
         "sdlc_stream_wait_event": (i32, [u64, u64]),
         "sdlc_event_synchronize": (i32, [u64]),
+        "sdlc_release_event": (None, [vp, u64]),
+        "sdlc_event_pool_size": (u64, [vp]),
         "sdlc_check_error": (ctypes.c_uint, [vp]),
         "sdlc_clear_error": (None, [vp]),
         "sdlc_launch_count": (u64, [vp]),
@@ -405,8 +407,26 @@ class SymmComm(object):
             raise CommError(self._err())
         return ev
 
-    def current_stream_wait(self, event):
+    def current_stream_wait(self, event, release=False):
+        """Make the current torch stream wait for ``event``; ``release=True`` hands the event back to the
+        pool afterwards (the caller will not use it again)."""
         self._lib.sdlc_stream_wait_event(torch.cuda.current_stream(self.device).cuda_stream, event)
+        if release:
+            self._lib.sdlc_release_event(self._h, event)
+
+    def release_event(self, event):
+        if event:
+            self._lib.sdlc_release_event(self._h, event)
+
+    def _stream_wait_current(self, stream):
+        """``stream`` waits for everything queued on the current torch stream so far."""
+        ev = self.record_ready_event()
+        self._lib.sdlc_stream_wait_event(stream, ev)
+        self._lib.sdlc_release_event(self._h, ev)
+
+    @property
+    def event_pool_size(self):
+        return self._lib.sdlc_event_pool_size(self._h)
 
     def check_error(self):
         e = self._lib.sdlc_check_error(self._h)
@@ -429,7 +449,7 @@ class SymmComm(object):
         lib = self._lib
         s = self.channel_stream(channel) if stream is None else stream
         if wait_current:
-            lib.sdlc_stream_wait_event(s, self.record_ready_event())
+            self._stream_wait_current(s)
         code = _TORCH_DTYPE[dtype] if isinstance(dtype, torch.dtype) else int(dtype)
         if wire:
             if op not in (_core.OP_SUM, _core.OP_AVERAGE):
@@ -492,7 +512,7 @@ class SymmComm(object):
             hyper["lr"] = float(group["lr"])
         if st is None:
             st = self.fused_state(opt, b)
-        lib.sdlc_stream_wait_event(s, self.record_ready_event())
+        self._stream_wait_current(s)
         rc = lib.sdlc_fused_step(
             self._h, 1, b.sym.id, b.psym.id, b.numel, code, ctypes.c_void_p(st["s1"].data_ptr()),
             ctypes.c_void_p(st["s2"].data_ptr() if st["s2"] is not None else 0),

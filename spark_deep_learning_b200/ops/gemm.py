@@ -1,13 +1,17 @@
-"""bf16 linear layer on the tcgen05 tensor cores with a fused bias / GELU epilogue
-(``csrc/cuda/gemm_tcgen05.cu``).
+"""bf16 GEMMs on the tcgen05 tensor cores with fused epilogues (``csrc/cuda/gemm_tcgen05.cu``).
 
-``linear_act(x, weight, bias, act)`` == ``act(F.linear(x, weight, bias))`` for bf16 operands.
-Forward runs the hand-written TMA -> tcgen05.mma -> TMEM -> epilogue kernel; backward uses plain
-library GEMMs (cuBLAS through torch.matmul) for dgrad / wgrad plus the analytic GELU derivative on
-the saved pre-activation.
+One hand-written kernel (CTA-pair tiles, TMA-fed, TMEM accumulators) runs all three GEMMs of a linear layer:
+
+* ``linear_act(x, weight, bias, act)`` == ``act(F.linear(x, weight, bias))``: forward with the bias / GELU epilogue,
+* dgrad ``dX = dY . W`` with the GELU derivative fused into the epilogue (no separate elementwise pass),
+* wgrad ``dW = dY^T . X`` (split-K over the tokens), optionally accumulated straight into a gradient buffer
+  (``wgrad_into``: the K11 path of SURVEY.md §2f - the weight gradient lands in the symmetric fusion bucket that the
+  reduce-scatter kernel reads, with no intermediate tensor and no autograd ``add_``),
+
+plus ``conv1x1_stats`` for NHWC 1x1 convolutions whose BatchNorm statistics come out of the GEMM epilogue.
+No operand is ever transposed in memory: the kernel takes K-major and MN-major operands.
 """
 import ctypes
-import os
 
 import torch
 
@@ -15,23 +19,25 @@ from spark_deep_learning_b200.ops import comm as _comm
 from spark_deep_learning_b200.utils import launch_counter
 
 ACT = {None: 0, "none": 0, "gelu_tanh": 1, "gelu": 2, "gelu_erf": 2}
+EPI_LINEAR, EPI_DGELU, EPI_ACC_BF16, EPI_ACC_F32, EPI_STATS = range(5)
 _sig = False
-# EXPERIMENTAL: 16-epilogue-warp kernel variant (gemm_tcgen05_epi16.cu), opt-in until it has been run on hardware
-_EPI16 = os.environ.get("SPARKDL_GEMM_EPI16", "0") == "1"
+_NUM_CLUSTERS = 74          # 148 SMs / 2
 
 
 def _lib():
     global _sig
     lib = _comm.load()
     if not _sig:
-        vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong
+        vp, i32, u64, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_longlong
         lib.sdlc_gemm_bf16.restype = i32
         lib.sdlc_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, u64]
+        lib.sdlc_gemm_ex.restype = i32
+        lib.sdlc_gemm_ex.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, vp, i32, i32, i32, i32, vp, i32, vp, i64,
+                                     i32, i32, vp, vp, i32, i32, u64]
         lib.sdlc_gelu_bwd.restype = i32
-        lib.sdlc_gelu_bwd.argtypes = [vp, vp, vp, ctypes.c_longlong, i32, u64]
-        if _EPI16:
-            lib.sdlc_gemm_bf16_epi16.restype = i32
-            lib.sdlc_gemm_bf16_epi16.argtypes = lib.sdlc_gemm_bf16.argtypes
+        lib.sdlc_gelu_bwd.argtypes = [vp, vp, vp, i64, i32, u64]
+        lib.sdlc_gemm_stat_rows.restype = i32
+        lib.sdlc_gemm_stat_rows.argtypes = [i32]
         _sig = True
     return lib
 
@@ -40,33 +46,130 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+_WS = {}
+
+
+def _workspace(device, nfloats):
+    """Grow-only fp32 scratch for split-K partial tiles (one per device)."""
+    ws = _WS.get(device)
+    if ws is None or ws.numel() < nfloats:
+        ws = torch.empty(max(nfloats, 1 << 22), dtype=torch.float32, device=device)
+        _WS[device] = ws
+    return ws
+
+
 def supported(x, weight):
     """True when the fused sm_100a kernel can take these arguments (device, dtype, layout, alignment)."""
     return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
             and x.shape[-1] % 8 == 0 and weight.shape[0] % 8 == 0 and weight.shape[1] == x.shape[-1])
 
 
-def gemm_bf16(x2d, weight, bias=None, act=None, save_pre_act=False, block_n=None):
-    """Raw kernel call: x2d [M,K] bf16, weight [N,K] bf16, bias fp32 [N] or None -> [M,N] bf16."""
+def _rowmajor(t):
+    """2-D tensor with unit inner stride and a 16-byte aligned pitch; returns (tensor, pitch)."""
+    if t.stride(1) != 1 or t.stride(0) % 8 != 0 or t.stride(0) < t.shape[1] or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+def gemm_ex(a, b, m, n, k, a_mn=False, b_mn=False, epi=EPI_ACC_BF16, out=None, out2=None, bias=None, act=None,
+            aux=None, accumulate=False, splits=1, stats=None, block_n=0):
+    """Raw kernel call: ``out[m,n] = epi(A . B^T)``.  ``a`` is stored [m,k] (K-major) or [k,m] (``a_mn``); ``b`` is
+    stored [n,k] or [k,n] (``b_mn``).  Returns ``out``."""
     lib = _lib()
-    x2d = x2d.contiguous()
-    weight = weight.contiguous()
+    a, lda = _rowmajor(a)
+    b, ldb = _rowmajor(b)
+    dev = a.device
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32 if epi == EPI_ACC_F32 else torch.bfloat16, device=dev)
+    ld_out = out.stride(0)
+    ws = None
+    if splits > 1:
+        ws = _workspace(dev, splits * ((m + 255) // 256) * 256 * n)
+    if bias is not None and bias.dtype != torch.float32:
+        bias = bias.float()
+    ld_aux = aux.stride(0) if aux is not None else 0
+    rc = lib.sdlc_gemm_ex(_p(a), lda, int(a_mn), _p(b), ldb, int(b_mn), _p(out), ld_out, _p(out2), m, n, k, epi,
+                          _p(bias), ACT[act] if not isinstance(act, int) else act, _p(aux), ld_aux, int(accumulate),
+                          splits, _p(ws), _p(stats), block_n, 0, _stream(a))
+    if rc != 0:
+        raise RuntimeError("sdlc_gemm_ex failed (%d) for M=%d N=%d K=%d epi=%d" % (rc, m, n, k, epi))
+    launch_counter.add(1 + (1 if splits > 1 else 0) + (1 if epi == EPI_STATS else 0))
+    return out
+
+
+def gemm_bf16(x2d, weight, bias=None, act=None, save_pre_act=False, block_n=None):
+    """Forward: x2d [M,K] bf16, weight [N,K] bf16, bias fp32 [N] or None -> ([M,N] bf16, pre-activation or None)."""
     m, k = x2d.shape
     n = weight.shape[0]
     out = torch.empty((m, n), dtype=torch.bfloat16, device=x2d.device)
     pre = torch.empty_like(out) if save_pre_act else None
-    if bias is not None and bias.dtype != torch.float32:
-        bias = bias.float()
-    if block_n is None:
-        # enough tiles to fill 148 SMs with the wide tile? otherwise use the narrow one
-        block_n = 256 if ((m + 127) // 128) * ((n + 255) // 256) >= 148 else 128
-    fn = lib.sdlc_gemm_bf16_epi16 if _EPI16 else lib.sdlc_gemm_bf16
-    rc = fn(_p(x2d), _p(weight), _p(bias), _p(out), _p(pre), m, n, k, ACT[act], block_n, 0,
-            torch.cuda.current_stream(x2d.device).cuda_stream)
-    if rc != 0:
-        raise RuntimeError("sdlc_gemm_bf16 failed (%d) for M=%d N=%d K=%d" % (rc, m, n, k))
-    launch_counter.add(1)
+    gemm_ex(x2d, weight, m, n, k, epi=EPI_LINEAR, out=out, out2=pre, bias=bias, act=act, block_n=block_n or 0)
     return out, pre
+
+
+def dgrad(dy2d, weight, pre=None, act=None):
+    """``dX[M,K_in] = (dY . W) [* gelu'(pre)]``: dy2d [M,N_out] bf16, weight [N_out,K_in] bf16 (read as an MN-major B)."""
+    m, n_out = dy2d.shape
+    k_in = weight.shape[1]
+    if pre is not None:
+        return gemm_ex(dy2d, weight, m, k_in, n_out, b_mn=True, epi=EPI_DGELU, aux=pre, act=act)
+    return gemm_ex(dy2d, weight, m, k_in, n_out, b_mn=True, epi=EPI_ACC_BF16)
+
+
+def _wgrad_splits(n_out, k_in, tokens):
+    tiles = ((n_out + 255) // 256) * ((k_in + 255) // 256)
+    kb = (tokens + 63) // 64
+    s = max(1, _NUM_CLUSTERS // max(tiles, 1))
+    return max(1, min(s, kb // 4, 16))
+
+
+def wgrad(dy2d, x2d, out=None, accumulate=False):
+    """``dW[N_out,K_in] (+)= dY^T . X`` without transposing anything: both operands are read MN-major.  ``out`` may be
+    bf16 or fp32 (e.g. a view of a gradient bucket)."""
+    tokens, n_out = dy2d.shape
+    k_in = x2d.shape[1]
+    if out is None:
+        out = torch.empty((n_out, k_in), dtype=torch.bfloat16, device=dy2d.device)
+    epi = EPI_ACC_F32 if out.dtype == torch.float32 else EPI_ACC_BF16
+    return gemm_ex(dy2d, x2d, n_out, k_in, tokens, a_mn=True, b_mn=True, epi=epi, out=out, accumulate=accumulate,
+                   splits=_wgrad_splits(n_out, k_in, tokens))
+
+
+def conv1x1_stats(x2d, weight):
+    """NHWC 1x1 convolution as a GEMM (``x2d`` [N*H*W, Cin], ``weight`` [Cout, Cin]) whose epilogue also produces
+    the per-channel sum and sum of squares of the bf16 output.  Returns (y [M,Cout] bf16, totals fp32 [2,Cout])."""
+    m, k = x2d.shape
+    n = weight.shape[0]
+    rows = _lib().sdlc_gemm_stat_rows(m)
+    stats = torch.empty((2 * rows + 2) * n, dtype=torch.float32, device=x2d.device)
+    y = gemm_ex(x2d, weight, m, n, k, epi=EPI_STATS, stats=stats)
+    return y, stats[2 * rows * n:].view(2, n)
+
+
+def gelu_bwd(dy2d, pre, act):
+    """``dy2d * gelu'(pre)`` as a stand-alone pass (when the product is needed as a GEMM operand)."""
+    g = torch.empty_like(pre)
+    rc = _lib().sdlc_gelu_bwd(_p(dy2d.contiguous()), _p(pre), _p(g), pre.numel(), 1 if act == "gelu_tanh" else 2, _stream(pre))
+    if rc != 0:
+        raise RuntimeError("sdlc_gelu_bwd failed")
+    launch_counter.add(1)
+    return g
+
+
+def _grad_sink(weight):
+    """The buffer the weight gradient should be accumulated into directly, or None.
+
+    ``DistributedOptimizer`` keeps ``weight.grad`` as a view of its symmetric gradient bucket and marks the parameter
+    with ``_sparkdl_grad_sink`` (a callable ``(param) -> None`` that plays the role of the post-accumulate hook).
+    """
+    sink = getattr(weight, "_sparkdl_grad_sink", None)
+    if sink is None or weight.grad is None or not weight.grad.is_contiguous():
+        return None
+    return sink
 
 
 class _LinearAct(torch.autograd.Function):
@@ -85,23 +188,70 @@ class _LinearAct(torch.autograd.Function):
     def backward(ctx, dy):
         x2d, weight, pre = ctx.saved_tensors
         dy2d = dy.reshape(-1, dy.shape[-1])
-        if pre is not None:
-            dy2d = dy2d.contiguous()
-            g = torch.empty_like(pre)
-            rc = _lib().sdlc_gelu_bwd(_p(dy2d), _p(pre), _p(g), pre.numel(), 1 if ctx.act == "gelu_tanh" else 2,
-                                      torch.cuda.current_stream(pre.device).cuda_stream)
-            if rc != 0:
-                raise RuntimeError("sdlc_gelu_bwd failed")
-            launch_counter.add(1)
-            dy2d = g
-        dx = dy2d @ weight                                   # dgrad: plain library GEMM
-        dw = dy2d.t() @ x2d                                  # wgrad: plain library GEMM
-        db = dy2d.sum(0, dtype=torch.float32) if ctx.has_bias else None
-        return dx.view(ctx.x_shape), dw, db, None
+        dy2d, _ = _rowmajor(dy2d)
+        need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        if pre is not None and (need_dw or need_db):
+            # dY * gelu'(pre) is needed as an operand of wgrad as well: materialise it once
+            dy2d = gelu_bwd(dy2d, pre, ctx.act)
+            pre = None
+        dx = dgrad(dy2d, weight, pre, ctx.act).view(ctx.x_shape) if need_dx else None
+        dw = None
+        if need_dw:
+            sink = _grad_sink(weight)
+            if sink is not None:
+                # K11: the wgrad epilogue accumulates straight into the gradient bucket; autograd sees no tensor
+                wgrad(dy2d, x2d, out=weight.grad, accumulate=True)
+                sink(weight)
+            else:
+                dw = wgrad(dy2d, x2d)
+        db = dy2d.sum(0, dtype=torch.float32) if need_db else None
+        return dx, dw, db, None
+
+
+class _MLP(torch.autograd.Function):
+    """``act(x W1^T + b1) W2^T + b2`` as one autograd node, so that the GELU derivative is applied inside the epilogue
+    of the second layer's dgrad GEMM (``dZ = (dY . W2) * gelu'(Z)``) instead of a separate elementwise pass."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, act):
+        x2d = x.reshape(-1, x.shape[-1])
+        h, z = gemm_bf16(x2d, w1, b1, act, save_pre_act=True)
+        y, _ = gemm_bf16(h, w2, b2, None)
+        ctx.save_for_backward(x2d, w1, w2, z, h)
+        ctx.act = act
+        ctx.x_shape = x.shape
+        ctx.has_b = (b1 is not None, b2 is not None)
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w1, w2, z, h = ctx.saved_tensors
+        dy2d, _ = _rowmajor(dy.reshape(-1, dy.shape[-1]))
+        dz = dgrad(dy2d, w2, z, ctx.act)                     # fused: (dY . W2) * gelu'(Z)
+        grads = {}
+        for name, w, g, inp in (("w2", w2, dy2d, h), ("w1", w1, dz, x2d)):
+            sink = _grad_sink(w)
+            if sink is not None:
+                wgrad(g, inp, out=w.grad, accumulate=True)
+                sink(w)
+                grads[name] = None
+            else:
+                grads[name] = wgrad(g, inp)
+        db2 = dy2d.sum(0, dtype=torch.float32) if ctx.has_b[1] else None
+        db1 = dz.sum(0, dtype=torch.float32) if ctx.has_b[0] else None
+        dx = dgrad(dz, w1).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        return dx, grads["w1"], db1, grads["w2"], db2, None
+
+
+def mlp(x, w1, b1, w2, b2, act="gelu"):
+    """Transformer feed-forward block ``act(x W1^T + b1) W2^T + b2`` (bf16), six tcgen05 GEMMs per fwd+bwd."""
+    if not (supported(x, w1) and w2.dtype == torch.bfloat16 and w2.shape[0] % 8 == 0 and w1.shape[0] % 8 == 0):
+        return linear_act(linear_act(x, w1, b1, act), w2, b2, None)
+    return _MLP.apply(x, w1, b1, w2, b2, act)
 
 
 def linear_act(x, weight, bias=None, act=None):
-    """``act(x @ weight.T + bias)``; bf16 in / out, fp32 accumulate, tcgen05 forward."""
+    """``act(x @ weight.T + bias)``; bf16 in / out, fp32 accumulate, all three GEMMs on the tcgen05 kernel."""
     if not supported(x, weight):
         y = torch.nn.functional.linear(x, weight, None if bias is None else bias.to(x.dtype))
         if act in ("gelu", "gelu_erf"):

@@ -7,10 +7,12 @@ Resolves the three bootstrap modes (SURVEY.md §5.8 "Bootstrap"):
    store on a unix socket whose name is derived from ``MASTER_PORT``;
 3. plain single process         - size 1, in-memory store.
 """
+import atexit
 import os
+import stat
 import threading
 
-from spark_deep_learning_b200.parallel.store import (LocalStore, StoreClient, StoreServer)
+from spark_deep_learning_b200.parallel.store import (LocalStore, NamespacedStore, StoreClient, StoreServer)
 
 _lock = threading.Lock()
 _ctx = None
@@ -39,10 +41,13 @@ class JobContext(object):
                              env.get("TORCHELASTIC_RUN_ID", "none"))
             tag = "".join(c if c.isalnum() or c in "-_" else "_" for c in tag)[:48]
             self.job_id = "ext" + tag
-            self.job_dir = "/tmp/sparkdl-ext-%s" % tag
-            path = "/tmp/sparkdl-store-%s.sock" % tag
+            # The store speaks pickle, so it must only be reachable by this user: a 0700 directory owned by us
+            # (under $XDG_RUNTIME_DIR when there is one) holds the socket and the fd-passing sockets.
+            base = env.get("XDG_RUNTIME_DIR") or "/tmp"
+            self.job_dir = os.path.join(base, "sparkdl-ext-%d-%s" % (os.getuid(), tag))
+            path = os.path.join(self.job_dir, "store.sock")
             if self.rank == 0:
-                os.makedirs(self.job_dir, exist_ok=True)
+                _private_dir(self.job_dir)
                 self._server = StoreServer(path)
             self.store = StoreClient(path)
             # Every rank must see the job dir before using it for fd sockets.
@@ -70,12 +75,32 @@ class JobContext(object):
             self._server = None
 
 
+def _private_dir(path):
+    """Create ``path`` with mode 0700, or insist that an existing one is ours and not group/world accessible."""
+    try:
+        os.mkdir(path, 0o700)
+    except FileExistsError:
+        st = os.lstat(path)
+        if not stat.S_ISDIR(st.st_mode) or st.st_uid != os.getuid():
+            raise RuntimeError("refusing to use %s: not a directory owned by uid %d" % (path, os.getuid()))
+        if st.st_mode & 0o077:
+            os.chmod(path, 0o700)
+
+
 def get_context():
+    """The process-wide job context.  It outlives ``hvd.shutdown()`` (the store connection is the only way
+    back to the driver / rank 0, and a later ``hvd.init()`` needs it); ``atexit`` closes it."""
     global _ctx
     with _lock:
         if _ctx is None:
             _ctx = JobContext()
+            atexit.register(reset_context)
         return _ctx
+
+
+def generation_store(ctx, generation):
+    """The job store seen through the key namespace of this ``hvd.init()`` generation."""
+    return NamespacedStore(ctx.store, "g%d/" % generation)
 
 
 def reset_context():

@@ -67,8 +67,18 @@ def load():
         lib.sdl_timeline_stop.argtypes = [vp]
     if hasattr(lib, "sdl_gbdt_hist_cpu"):          # absent only in a stale in-tree build
         lib.sdl_gbdt_hist_cpu.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32]
+    if hasattr(lib, "sdl_exit_watchdog"):
+        lib.sdl_exit_watchdog.argtypes = [dbl, i32]
+        lib.sdl_exit_watchdog.restype = None
     _LIB = lib
     return lib
+
+
+def exit_watchdog(seconds, code):
+    """Native detached thread that ``_exit(code)``s after ``seconds`` unless the process has left by itself."""
+    lib = load()
+    if hasattr(lib, "sdl_exit_watchdog"):
+        lib.sdl_exit_watchdog(float(seconds), int(code))
 
 
 class EngineError(RuntimeError):

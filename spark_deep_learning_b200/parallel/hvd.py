@@ -77,6 +77,12 @@ def init(comm=None, process_sets=None):  # pylint: disable=unused-argument
             return
         cfg = get_config(refresh=True)
         ctx = _context.get_context()
+        # re-init support (Horovod allows shutdown() -> init()): every incarnation talks to the store through its
+        # own key namespace, so stale bootstrap keys of the previous one are never observed.
+        _S.generation = getattr(_S, "generation", 0) + 1
+        if getattr(ctx, "base_store", None) is None:
+            ctx.base_store = ctx.store
+        ctx.store = _context.NamespacedStore(ctx.base_store, "g%d/" % _S.generation)
         use_cuda = torch.cuda.is_available() and os.environ.get("SPARKDL_FORCE_CPU") != "1"
         if use_cuda:
             torch.cuda.set_device(ctx.local_rank % torch.cuda.device_count())
@@ -111,8 +117,12 @@ def shutdown():
                 _S.engine.shutdown()
             finally:
                 _S.engine = None
-                _context.reset_context()
-                _S.ctx = None
+                _S.ctx = None   # the job context (store connection) stays alive for a later init()
+
+
+def rank_hint():
+    """Rank of this process as the launcher assigned it; usable before ``init()`` / after ``shutdown()``."""
+    return _context.get_context().rank
 
 
 def is_initialized():
@@ -430,7 +440,14 @@ def synchronize(handle):
             if handle.cuda:
                 ev = _S.engine.done_event(h)
                 if ev:
-                    _S.comm.current_stream_wait(ev)
+                    _S.comm.current_stream_wait(ev, release=True)
+        if handle.cuda:
+            # a peer that stopped after negotiation makes the kernel's flag barrier time out; surface that
+            # instead of returning partial data
+            try:
+                _S.comm.check_error()
+            except Exception as e:  # pylint: disable=broad-except
+                raise HorovodInternalError(str(e))
         out = handle.output
         if handle.post is not None:
             out = handle.post(handle)

@@ -258,12 +258,12 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 hvd.synchronize(b.handle)
                 b.handle = None
             if b.done_event:
-                comm.current_stream_wait(b.done_event)
+                comm.current_stream_wait(b.done_event, release=True)
                 b.done_event = 0
         if self._fused and comm is not None:
             ev = comm.fused_step_advance(self)
             if ev:
-                comm.current_stream_wait(ev)      # also re-joins the channel stream under graph capture
+                comm.current_stream_wait(ev, release=True)   # also re-joins the channel stream under graph capture
         if comm is not None:
             comm.check_error()                    # a peer-wait timeout of an earlier launch (host-mapped flag, no sync)
         self._synchronized = True

@@ -238,6 +238,35 @@ class LocalStore(object):
         pass
 
 
+class NamespacedStore(object):
+    """View of a store with every key prefixed.  ``hvd.init()`` wraps the job store in
+    ``NamespacedStore(store, "g<N>/")`` with N = how many times this process has initialised, so a
+    ``shutdown()`` -> ``init()`` cycle never reads the bootstrap keys (shm segment name, IPC handles, votes,
+    barrier counters) of the previous incarnation."""
+
+    def __init__(self, base, prefix):
+        self._base = base
+        self._prefix = prefix
+
+    def set(self, key, value):
+        return self._base.set(self._prefix + key, value)
+
+    def get(self, key, *args, **kwargs):
+        return self._base.get(self._prefix + key, *args, **kwargs)
+
+    def try_get(self, key, default=None):
+        return self._base.try_get(self._prefix + key, default)
+
+    def add(self, key, amount=1):
+        return self._base.add(self._prefix + key, amount)
+
+    def log(self, rank, message):
+        return self._base.log(rank, message)
+
+    def close(self):
+        pass   # the base store belongs to the job context
+
+
 def store_barrier(store, name, rank, size, timeout=300.0):
     """Counter barrier on the store (cold path only: init / shutdown / handle exchange)."""
     if size <= 1:

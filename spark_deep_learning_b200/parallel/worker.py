@@ -43,6 +43,30 @@ def _maybe_inject_fault(rank, where):
         time.sleep(float(opts.get("seconds", 3600)))
 
 
+def _pin_device():
+    """Bind this task slot to its GPU *before* user code runs (``runner_base.py:44-45``: a task slot
+    "maps to a GPU"), so a ``main`` that touches CUDA before ``hvd.init()`` still lands on its own device.
+    All GPUs stay visible (peer access needs them), so this is ``set_device``, not CUDA_VISIBLE_DEVICES."""
+    if os.environ.get("SPARKDL_FORCE_CPU") == "1" or os.environ.get("SPARKDL_NO_PIN") == "1":
+        return
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("SPARKDL_LOCAL_RANK", "0")) % torch.cuda.device_count())
+    except Exception:  # pylint: disable=broad-except
+        pass
+
+
+def _arm_exit_watchdog(code, seconds=20.0):
+    """Leave through the normal interpreter shutdown (at-exit hooks run, unlike ``os._exit``); a native
+    detached thread ends the process if that shutdown wedges."""
+    try:
+        from spark_deep_learning_b200.parallel import core as _core
+        _core.exit_watchdog(seconds, code)
+    except Exception:  # pylint: disable=broad-except
+        pass
+
+
 def main():
     rank = int(os.environ["SPARKDL_RANK"])
     job_dir = os.environ["SPARKDL_JOB_DIR"]
@@ -52,6 +76,7 @@ def main():
     try:
         import cloudpickle
         _maybe_inject_fault(rank, "start")
+        _pin_device()
         with open(os.path.join(job_dir, "payload.pkl"), "rb") as f:
             fn, kwargs = cloudpickle.load(f)
         result = fn(**kwargs)
@@ -87,4 +112,5 @@ if __name__ == "__main__":
     code = main()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(code)
+    _arm_exit_watchdog(code)
+    sys.exit(code)

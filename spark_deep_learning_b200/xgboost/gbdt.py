@@ -466,7 +466,8 @@ def compute_cuts(X, missing, max_bin, dist, sample_rows=200000, seed=0):
     if dist.size > 1:
         S = dist.allgather(S.contiguous())
     miss_nan = isinstance(missing, float) and math.isnan(missing)
-    n_cuts = min(max_bin, MAX_BINS) - 1
+    # c cuts make c + 1 real bins 0..c; bin 255 is reserved for missing values, so at most 254 cuts
+    n_cuts = min(max_bin, MAX_BINS - 1) - 1
     cuts = []
     qs = torch.linspace(0, 1, n_cuts + 2, device=S.device)[1:-1]
     for f in range(F):
@@ -492,6 +493,7 @@ def bin_features(X, cuts, missing):
         col = X[:, f].contiguous()
         b = torch.searchsorted(cuts[f], col, right=True) if cuts[f].numel() else torch.zeros(n, dtype=torch.long, device=X.device)
         m = torch.isnan(col) if miss_nan else ((col == missing) | torch.isnan(col))
+        b = b.clamp_(max=MISSING_BIN - 1)   # a real value never lands in the missing bin
         B[:, f] = torch.where(m, torch.full_like(b, MISSING_BIN), b).to(torch.uint8)
     return B.contiguous()
 

@@ -551,3 +551,25 @@ def test_collectives_fuzz_random_shapes_dtypes_and_splits():
         return bad
     bad = HorovodRunner(np=-3).run(main, cases=150, seed=11)
     assert bad == [], bad[:5]
+
+
+def test_shutdown_then_init_in_the_same_job():
+    """Horovod supports re-init; every incarnation must bootstrap through its own store-key
+    namespace (rank 0 deliberately arrives late so a stale 'shm_name' would be picked up by rank 1)."""
+    def main():
+        import time
+        import torch
+        import sparkdl.hvd as hvd
+        out = []
+        for gen in range(3):
+            if gen and hvd.rank_hint() == 0:
+                time.sleep(1.0)
+            hvd.init()
+            r, n = hvd.rank(), hvd.size()
+            s = hvd.allreduce(torch.full((17,), float(r + gen)), op=hvd.Sum, name="reinit")
+            out.append(float(s[0]))
+            hvd.barrier()
+            hvd.shutdown()
+        return out
+    res = HorovodRunner(np=-2).run(main)
+    assert res == [1.0, 3.0, 5.0]

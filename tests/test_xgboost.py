@@ -540,3 +540,21 @@ def test_spark_dataframe_adapter_with_a_duck_typed_frame():
     pdf = out.toPandas()
     ref = XgboostRegressor(n_estimators=10, max_depth=3).fit(pd.DataFrame({"features": list(X), "label": y}))
     assert np.allclose(pdf["prediction"], ref.transform(pd.DataFrame({"features": list(X)}))["prediction"])
+
+
+def test_real_values_never_land_in_the_missing_bin():
+    """with max_bin=256 the top quantile used to be binned as 255 == MISSING_BIN, so training
+    routed those rows by default_left while inference routed them by value."""
+    import torch
+    from spark_deep_learning_b200.xgboost import gbdt
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(5000, 3, generator=g)
+    dist = gbdt._Dist()
+    cuts = gbdt.compute_cuts(X, float("nan"), 256, dist)
+    assert max(c.numel() for c in cuts) <= gbdt.MISSING_BIN - 1
+    bins = gbdt.bin_features(X, cuts, float("nan"))
+    assert int((bins == gbdt.MISSING_BIN).sum()) == 0
+    X[::7, 1] = float("nan")
+    bins = gbdt.bin_features(X, cuts, float("nan"))
+    assert int((bins[:, 1] == gbdt.MISSING_BIN).sum()) == int(torch.isnan(X[:, 1]).sum())
+    assert int((bins[:, 0] == gbdt.MISSING_BIN).sum()) == 0
