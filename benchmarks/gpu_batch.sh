@@ -27,6 +27,13 @@ for stage in "$@"; do
                (timeout 300 python benchmarks/bert_probe.py 2>&1 | tail -30) > gpurun_out/bert_probe.txt
                tail -12 gpurun_out/resnet_probe.txt gpurun_out/bert_probe.txt ;;
     xgb)       (timeout 400 python benchmarks/xgboost_bench.py --np 1 2>&1 | tail -8) > gpurun_out/xgb_np1.txt; cat gpurun_out/xgb_np1.txt ;;
+    profbert)  (timeout 300 python benchmarks/step_profile.py bert 2>&1 | tail -5) > gpurun_out/step_profile_bert.log; cat gpurun_out/step_profile_bert.log ;;
+    profresnet) (timeout 300 python benchmarks/step_profile.py resnet 2>&1 | tail -5) > gpurun_out/step_profile_resnet.log; cat gpurun_out/step_profile_resnet.log ;;
+    bertprobe) (timeout 200 python benchmarks/bert_sink_probe.py 2>&1 | tail -40) > gpurun_out/bert_sink_probe.txt; tail -25 gpurun_out/bert_sink_probe.txt ;;
+    gemmstaging) for d in 1 2; do (SPARKDL_GEMM_STAGING=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | sed "s/^dbg=0/staging=$d/" | tail -10); done > gpurun_out/gemm_staging.txt; cat gpurun_out/gemm_staging.txt ;;
+    gemmlab)   for d in 0 1 2 3 4; do (SPARKDL_GEMM_DBG=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | grep -v cublas | tail -8); done > gpurun_out/gemm_lab.txt
+               (timeout 120 python benchmarks/gemm_lab.py 2>&1 | grep cublas) >> gpurun_out/gemm_lab.txt; cat gpurun_out/gemm_lab.txt ;;
+    gemmncu)   timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -c 6 -f -o gpurun_out/prof_gemm2 python benchmarks/gemm_lab.py ncu > gpurun_out/ncu_gemm2.log 2>&1; tail -3 gpurun_out/ncu_gemm2.log ;;
     *)         echo "unknown stage $stage" ;;
   esac
 done

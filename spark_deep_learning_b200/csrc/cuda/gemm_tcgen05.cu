@@ -37,6 +37,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace gemm {
@@ -49,7 +50,8 @@ constexpr int kNumThreads = 384; // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;     // two warps per TMEM lane quarter, each owning half of the tile's columns
 constexpr int kStageBufBytes = 4096;                       // 32 rows x 128 bytes
-constexpr int kStagingBytes = kEpiWarps * 2 * kStageBufBytes;
+constexpr int kMaxStages = 8;
+constexpr int kMaxSmem = 232448;                           // 227 KB: the opt-in maximum per CTA
 constexpr int kGroupM = 8;       // raster group: this many M-tiles walk the N-tiles together
 
 enum { EPI_LINEAR = 0, EPI_DGELU = 1, EPI_ACC_BF16 = 2, EPI_ACC_F32 = 3, EPI_STATS = 4 };
@@ -60,8 +62,14 @@ struct Cfg {
   static constexpr int kABytes = CTA_M * BLOCK_K * 2;        // 16 KB
   static constexpr int kBBytes = kBRows * BLOCK_K * 2;       // 16 KB (BLOCK_N 256) / 8 KB (128)
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BLOCK_N == 256 ? 5 : 6;
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+  // shared memory: stages x (A + B) | 8 warps x staging_bufs x 4 KB | barriers; the ring takes what staging leaves
+  static constexpr int smem_bytes(int stages, int staging_bufs) {
+    return stages * kStageBytes + kEpiWarps * staging_bufs * kStageBufBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+  }
+  static constexpr int max_stages(int staging_bufs) {
+    int s = (kMaxSmem - smem_bytes(0, staging_bufs)) / kStageBytes;
+    return s > kMaxStages ? kMaxStages : s;
+  }
 };
 
 struct GemmParams {
@@ -77,6 +85,8 @@ struct GemmParams {
   long long ld_aux;
   float* stats;                // STATS: partial sums [2][stat_rows][N] (sum, then sum of squares)
   int stat_rows;               // STATS: number of 32-row groups = m_tiles * 8
+  int stages, staging_bufs;    // smem ring depth; staging buffers per epilogue warp (1 or 2)
+  int dbg;                     // lab switches (SPARKDL_GEMM_DBG): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue stores
 };
 
 // ---------------- PTX wrappers -----------------------------------------------------------------------------------
@@ -105,9 +115,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on an mbarrier that lives in another CTA of the cluster (address from mapa)
+// arrive on an mbarrier that lives in another CTA of the cluster (address from mapa).  Default semantics
+// (.release.cta): a .release.cluster here compiles to MEMBAR.ALL.GPU + ERRBAR per arrival, which serialised the
+// producer of the non-leader CTA behind its own in-flight TMA loads (ncu source page, round 2) - the data hand-off
+// itself is ordered by complete_tx (TMA) and by tcgen05.fence (TMEM), not by this arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -256,15 +269,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   // identical layout in both CTAs of the pair (the MMA addresses both through one descriptor)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using C = Cfg<BLOCK_N>;
-  constexpr int kStages = C::kStages;
+  const int kStages = p.stages;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * C::kABytes;
   uint8_t* staging = smem + kStages * C::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
-  uint64_t* full = bars;                    // [kStages]  used in the leader CTA: 2 arrivals + both CTAs' TMA bytes
-  uint64_t* empty = bars + kStages;         // [kStages]  one per CTA, released by the multicast commit
-  uint64_t* tmem_full = bars + 2 * kStages; // [2]        one per CTA, multicast commit
-  uint64_t* tmem_empty = tmem_full + 2;     // [2]        used in the leader CTA: 16 epilogue warps of the pair
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiWarps * p.staging_bufs * kStageBufBytes);
+  uint64_t* full = bars;                       // [kMaxStages] used in the leader CTA: 2 arrivals + both CTAs' TMA bytes
+  uint64_t* empty = bars + kMaxStages;         // [kMaxStages] one per CTA, released by the multicast commit
+  uint64_t* tmem_full = bars + 2 * kMaxStages; // [2]          one per CTA, multicast commit
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]          used in the leader CTA: 16 epilogue warps of the pair
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -315,6 +328,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t bar = mapa(smem_u32(&full[stage]), 0);
           const uint32_t sa = smem_u32(smem_a + stage * C::kABytes), sb = smem_u32(smem_b + stage * C::kBBytes);
+          if (p.dbg & 1) {
+            if (leader) mbar_arrive(&full[stage]);
+            else mbar_arrive_cluster(bar);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (!p.a_mn) {
             tma_load_2d(sa, &map_a, bar, kb * BLOCK_K, a_row);
           } else {
@@ -359,7 +378,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t da = make_smem_desc(a_addr + k * a_kstep, a_lbo);
               const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo);
-              umma_f16_2cta(tmem_d, da, db, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+              if (!(p.dbg & 2)) umma_f16_2cta(tmem_d, da, db, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
             }
             umma_commit_2cta(&empty[stage]);           // frees this smem slot in both CTAs when the MMAs retire
             if (kb == w.kb1 - 1) umma_commit_2cta(&tmem_full[acc]);
@@ -383,15 +402,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int half = e >> 2;                         // which half of the tile's columns this warp drains
     constexpr int kColsPerWarp = BLOCK_N / 2;
     constexpr int kChunk = (EPI == EPI_ACC_F32) ? 32 : 64;   // columns per staged box (128-byte rows)
-    uint8_t* stage_buf = staging + e * (2 * kStageBufBytes);
+    const int nbufs = p.staging_bufs;
+    uint8_t* stage_buf = staging + e * (nbufs * kStageBufBytes);
     int sbuf = 0;
     const uint32_t tmem_empty_leader = mapa(smem_u32(&tmem_empty[0]), 0);
 
     // registers -> staging buffer (thread = row; 16-byte chunk j of row r lives at chunk j ^ (r & 7), the layout a
     // SWIZZLE_128B tensor map expects) -> one TMA store of the 32-row box
     auto store_box = [&](const uint4* o, const CUtensorMap* map, int col, int row) {
+      if (p.dbg & 4) return;
       uint8_t* buf = stage_buf + sbuf * kStageBufBytes;
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that used `buf` has read it
+      if (lane == 0) {   // the store that used `buf` last has finished reading it
+        if (nbufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
@@ -401,7 +425,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         tma_store_2d(map, smem_u32(buf), col, row);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      sbuf ^= 1;
+      sbuf = (nbufs == 2) ? (sbuf ^ 1) : 0;
     };
     auto store_bf16 = [&](const float* f, const CUtensorMap* map, int col, int row) {
       uint4 o[8];
@@ -661,10 +685,10 @@ static bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, 
 template <int BLOCK_N, int EPI>
 static cudaError_t launch(int grid, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
                           const CUtensorMap& mo2, const GemmParams& p) {
-  constexpr int smem = Cfg<BLOCK_N>::kSmem;
+  const int smem = Cfg<BLOCK_N>::smem_bytes(p.stages, p.staging_bufs);
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
@@ -739,6 +763,15 @@ int sdlc_gemm_ex(const void* a, long long lda, int a_mn, const void* b, long lon
   p.accumulate = (accumulate && splits == 1) ? 1 : 0;
   if (p.accumulate && acc_epi) { p.aux = out; p.ld_aux = ld_out; }
   p.stats = stats; p.stat_rows = m_tiles * 8;
+  static int dbg = -1, staging_env = -1;
+  if (dbg < 0) { const char* e = getenv("SPARKDL_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+  if (staging_env < 0) { const char* e = getenv("SPARKDL_GEMM_STAGING"); staging_env = e ? atoi(e) : 0; }
+  p.dbg = dbg;
+  // a deeper operand ring beats double-buffered epilogue staging when the K loop is long; EPI_STATS reads its
+  // staging buffer back after the store was issued, so it keeps two
+  p.staging_bufs = (staging_env == 1 || staging_env == 2) ? staging_env : 1;
+  if (epi == EPI_STATS) p.staging_bufs = 2;
+  p.stages = block_n == 256 ? Cfg<256>::max_stages(p.staging_bufs) : Cfg<128>::max_stages(p.staging_bufs);
   if (epi == EPI_STATS && !stats) return -2;
   if (epi == EPI_DGELU && (!aux || (ld_aux % 8) != 0)) return -2;
 

@@ -1,8 +1,9 @@
 """BERT-large for pre-training (MLM + NSP), BASELINE.json config 3.
 
-Every projection (QKV, attention output, FFN up with fused bias+GELU, FFN down, MLM transform and the
-30k-wide vocabulary decoder) runs through :func:`spark_deep_learning_b200.ops.gemm.linear_act`, i.e. the
-hand-written tcgen05 GEMM with the bias / GELU epilogue fused.  Attention itself is the library
+Every projection (QKV, attention output, the FFN block, MLM transform and the 30k-wide vocabulary decoder) runs
+forward AND backward through :mod:`spark_deep_learning_b200.ops.gemm`, i.e. the hand-written CTA-pair tcgen05 GEMM:
+bias / GELU fused into the forward epilogue, GELU' fused into the dgrad epilogue, and the weight gradients accumulated
+straight into the DistributedOptimizer's symmetric gradient buckets by the wgrad epilogue.  Attention itself is the library
 flash kernel behind ``F.scaled_dot_product_attention``.  Parameters are bf16; the fused
 DistributedOptimizer keeps fp32 master weights and Adam moments, sharded 1/N per GPU.
 """
@@ -49,7 +50,11 @@ class Layer(nn.Module):
         a = F.scaled_dot_product_attention(q, k, v, dropout_p=self.p if self.training else 0.0)
         a = self.proj(a.transpose(1, 2).reshape(b, s, h))
         x = self.ln1(x, a)                       # LayerNorm(x + dropout(a)) in one pass
-        f = self.down(self.up(x))
+        if self.up.fused and x.is_cuda and x.dtype == torch.bfloat16:
+            # one autograd node: gelu' is applied inside the dgrad GEMM of the down projection
+            f = gemm.mlp(x, self.up.weight, self.up.bias, self.down.weight, self.down.bias, "gelu")
+        else:
+            f = self.down(self.up(x))
         return self.ln2(x, f)
 
 
@@ -85,7 +90,8 @@ class BertForPreTraining(nn.Module):
         bias = self.mlm_bias.float().clone()
         bias[self.vocab:] = -1e4                                   # padded vocabulary entries never win
         if self.fused and hmlm.is_cuda and hmlm.dtype == torch.bfloat16:
-            logits = gemm.linear_act(hmlm, self.word.weight, bias, None)   # tied decoder
+            # tied decoder: the embedding lookup also sends gradient to this matrix, so its wgrad stays on autograd
+            logits = gemm.linear_act(hmlm, self.word.weight, bias, None, direct_wgrad=False)
         else:
             logits = F.linear(hmlm, self.word.weight.to(hmlm.dtype), bias.to(hmlm.dtype))
         pooled = torch.tanh(self.pooler(x[:, 0]))

@@ -174,7 +174,8 @@ def _grad_sink(weight):
 
 class _LinearAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act):
+    def forward(ctx, x, weight, bias, act, use_sink=True):
+        ctx.use_sink = use_sink
         x2d = x.reshape(-1, x.shape[-1])
         need_pre = act not in (None, "none") and (x.requires_grad or weight.requires_grad)
         out, pre = gemm_bf16(x2d, weight, bias, act, save_pre_act=need_pre)
@@ -197,7 +198,7 @@ class _LinearAct(torch.autograd.Function):
         dx = dgrad(dy2d, weight, pre, ctx.act).view(ctx.x_shape) if need_dx else None
         dw = None
         if need_dw:
-            sink = _grad_sink(weight)
+            sink = _grad_sink(weight) if ctx.use_sink else None
             if sink is not None:
                 # K11: the wgrad epilogue accumulates straight into the gradient bucket; autograd sees no tensor
                 wgrad(dy2d, x2d, out=weight.grad, accumulate=True)
@@ -205,7 +206,7 @@ class _LinearAct(torch.autograd.Function):
             else:
                 dw = wgrad(dy2d, x2d)
         db = dy2d.sum(0, dtype=torch.float32) if need_db else None
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 class _MLP(torch.autograd.Function):
@@ -250,8 +251,11 @@ def mlp(x, w1, b1, w2, b2, act="gelu"):
     return _MLP.apply(x, w1, b1, w2, b2, act)
 
 
-def linear_act(x, weight, bias=None, act=None):
-    """``act(x @ weight.T + bias)``; bf16 in / out, fp32 accumulate, all three GEMMs on the tcgen05 kernel."""
+def linear_act(x, weight, bias=None, act=None, direct_wgrad=True):
+    """``act(x @ weight.T + bias)``; bf16 in / out, fp32 accumulate, all three GEMMs on the tcgen05 kernel.
+
+    ``direct_wgrad=False`` keeps the weight gradient on the autograd path (needed when ``weight`` also receives
+    gradient from another use in the same backward, e.g. a tied embedding / decoder matrix)."""
     if not supported(x, weight):
         y = torch.nn.functional.linear(x, weight, None if bias is None else bias.to(x.dtype))
         if act in ("gelu", "gelu_erf"):
@@ -259,4 +263,4 @@ def linear_act(x, weight, bias=None, act=None):
         if act == "gelu_tanh":
             return torch.nn.functional.gelu(y, approximate="tanh")
         return y
-    return _LinearAct.apply(x, weight, bias, act)
+    return _LinearAct.apply(x, weight, bias, act, direct_wgrad)

@@ -82,6 +82,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                              % ", ".join(str(i) for i in sorted(all_ids - named_ids)))
         self._names = {id(p): n for n, p in named_parameters}
         self._passes = {}
+        self._sunk = set()
         self._grad_ptr = {}
         self._buckets = []
         self._bucket_of = {}
@@ -161,7 +162,25 @@ class _DistributedOptimizer(torch.optim.Optimizer):
     def _register_hooks(self):
         for b in self._buckets:
             for p in b.params:
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook()))
+                hook = self._make_hook()
+                sunk = self._sunk
+
+                # K11: a wgrad GEMM may accumulate straight into ``p.grad`` (a view of this bucket) and then call
+                # the sink instead of handing autograd a tensor (ops/gemm.py::_grad_sink) - same bookkeeping, no
+                # intermediate dW tensor and no AccumulateGrad add.  autograd still visits the parameter's
+                # AccumulateGrad node with an undefined gradient and runs the post-accumulate hook (observed on
+                # torch 2.11), so that visit is swallowed once per sink call.
+                def sink(q, hook=hook, sunk=sunk):
+                    sunk.add(id(q))
+                    hook(q)
+
+                def from_autograd(q, hook=hook, sunk=sunk):
+                    if id(q) in sunk:
+                        sunk.discard(id(q))
+                        return
+                    hook(q)
+                self._hooks.append(p.register_post_accumulate_grad_hook(from_autograd))
+                p._sparkdl_grad_sink = sink
 
     def _make_hook(self):
         # Runs on the autograd thread once per parameter per backward: keep it to a pointer compare and
@@ -169,6 +188,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         passes = self._passes
         bucket_of = self._bucket_of
         expected = self._grad_ptr
+        names = self._names
 
         def hook(p):
             pid = id(p)
@@ -176,7 +196,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             if b.launched:
                 raise AssertionError(
                     "Gradients were computed more than backward_passes_per_step times before call "
-                    "to step(). Increase backward_passes_per_step to accumulate gradients locally.")
+                    "to step(). Increase backward_passes_per_step to accumulate gradients locally. "
+                    "(parameter %r, bucket %d, pass %d)" % (names.get(pid), b.index, passes[pid] + 1))
             g = p.grad
             if g is None:
                 return
@@ -293,6 +314,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             b.launched = False
         for k in self._passes:
             self._passes[k] = 0
+        self._sunk.clear()
         self._next_launch = 0
         self._synchronized = False
 

@@ -261,3 +261,123 @@ def test_fused_broadcast_optimizer_state_resume():
     """3 uninterrupted steps == 2 steps + checkpoint + (rank 0 loads, broadcast_*) + 1 step."""
     diff = HorovodRunner(np=_np()).run(_bcast_opt_state_main)
     assert diff < 1e-5, diff
+
+
+# ---------------------------------------------------------------------------------------------
+# T4 (SURVEY.md §4b): loss-curve equivalence of the whole fused path (bf16 weights + fp32 masters in the sharded fused
+# optimizer, fused BN / LayerNorm / tcgen05 GEMM kernels, CUDA graph) against torch DDP (fp32 masters, bf16 autocast,
+# torch.optim) from the SAME initial weights on the SAME data
+# ---------------------------------------------------------------------------------------------
+def _equivalence_main(model_name, steps):
+    import os
+    import torch
+    import torch.distributed as dist
+    import sparkdl.hvd as hvd
+    from spark_deep_learning_b200 import models
+    from spark_deep_learning_b200.models import bert as bert_mod
+    from spark_deep_learning_b200.utils.graph import GraphedTrainStep
+    hvd.init()
+    r, n = hvd.rank(), hvd.size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(4321)
+    g = torch.Generator().manual_seed(99 + r)                        # every rank its own shard of the data
+    if model_name == "resnet":
+        ours = models.resnet50(num_classes=100, fused=True, bf16_weights=True).to(dev).to(memory_format=torch.channels_last)
+        ref = models.resnet50(num_classes=100, fused=False).to(dev).to(memory_format=torch.channels_last)
+        ref.load_state_dict({k: v.float() for k, v in ours.state_dict().items()})
+        x = torch.randn(32, 3, 96, 96, generator=g).to(dev)
+        y = torch.randint(0, 100, (32,), generator=g).to(dev)
+        mk = lambda p: torch.optim.SGD(p, lr=0.02, momentum=0.9, weight_decay=1e-4)   # noqa: E731
+        crit = torch.nn.CrossEntropyLoss()
+
+        def fwd_ours(xx, yy):
+            return crit(ours(xx.to(dtype=torch.bfloat16, memory_format=torch.channels_last)).float(), yy)
+
+        def fwd_ref(xx, yy):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return crit(ddp(xx.contiguous(memory_format=torch.channels_last)).float(), yy)
+    else:
+        kw = dict(vocab=2000, hidden=256, layers=4, heads=4, ffn=1024, max_pos=128, dropout=0.0)
+        ours = bert_mod.BertForPreTraining(fused=True, **kw).to(torch.bfloat16).to(dev)
+        ref = bert_mod.BertForPreTraining(fused=False, **kw).to(dev)
+        ref.load_state_dict({k: v.float() for k, v in ours.state_dict().items()})
+        x = torch.randint(0, 2000, (16, 128), generator=g).to(dev)
+        y = torch.randint(0, 2000, (16, 128), generator=g).to(dev)
+        mk = lambda p: torch.optim.AdamW(p, lr=2e-4, weight_decay=0.01)   # noqa: E731
+
+        def fwd_ours(xx, yy):
+            return ours(xx, labels=yy)
+
+        def fwd_ref(xx, yy):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return ddp(xx, labels=yy)
+    opt = hvd.DistributedOptimizer(mk(ours.parameters()), named_parameters=ours.named_parameters(), fused=True)
+    hvd.broadcast_parameters(ours.state_dict(), root_rank=0)
+
+    def step(xx, yy):
+        opt.zero_grad()
+        loss = fwd_ours(xx, yy)
+        loss.backward()
+        opt.step()
+        return loss
+    graphed = GraphedTrainStep(step, (x, y), warmup=0) if os.environ.get("SPARKDL_T4_GRAPH", "1") == "1" else step
+    ours_curve = []
+    for _ in range(steps):
+        ours_curve.append(float(graphed(x, y)))
+    torch.cuda.synchronize()
+    hvd.comm_backend().check_error()
+    # the reference arm: stock DDP over NCCL in the same processes
+    dist.init_process_group("nccl", device_id=dev)
+    ddp = torch.nn.parallel.DistributedDataParallel(ref, device_ids=[dev.index])
+    ropt = mk(ref.parameters())
+    ref_curve = []
+    for _ in range(steps):
+        ropt.zero_grad()
+        loss = fwd_ref(x, y)
+        loss.backward()
+        ropt.step()
+        ref_curve.append(float(loss))
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    # rank-average both curves so the comparison is about the same global batch
+    c = hvd.allreduce(torch.tensor([ours_curve, ref_curve], dtype=torch.float64), name="curves")
+    return c[0].tolist(), c[1].tolist()
+
+
+@pytest.mark.parametrize("model_name,steps,tol", [("bert", 20, 0.03), ("resnet", 20, 0.06)])
+def test_loss_curve_matches_ddp(model_name, steps, tol):
+    ours, ref = HorovodRunner(np=-2).run(_equivalence_main, model_name=model_name, steps=steps)
+    print("ours", ["%.4f" % v for v in ours])
+    print("ddp ", ["%.4f" % v for v in ref])
+    assert abs(ours[0] - ref[0]) / ref[0] < 0.01, (ours[0], ref[0])           # same weights, same data
+    assert ref[-1] < ref[0]                                                     # the reference is learning
+    worst = max(abs(a - b) / b for a, b in zip(ours, ref))
+    assert worst < tol, (worst, ours, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# K8: distributed GBDT over the fused histogram + allreduce kernel == single-worker model, bit for bit
+# ---------------------------------------------------------------------------------------------
+def _gbdt_main(fused):
+    import os
+    import numpy as np
+    import torch
+    import sparkdl.hvd as hvd
+    from spark_deep_learning_b200.xgboost import gbdt
+    os.environ["SPARKDL_GBDT_FUSED"] = "1" if fused else "0"
+    hvd.init()
+    r, n = hvd.rank(), hvd.size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rng = np.random.RandomState(0)
+    X = rng.randn(40000, 24).astype(np.float32)
+    X[rng.rand(*X.shape) < 0.05] = np.nan
+    y = (X[:, 0] * 2 + np.sin(3 * np.nan_to_num(X[:, 1])) + (np.nan_to_num(X[:, 2]) > 0.3) + 0.1 * rng.randn(len(X))).astype(np.float32)
+    lo, hi = r * len(X) // n, (r + 1) * len(X) // n
+    params = dict(n_estimators=8, max_depth=5, learning_rate=0.3, max_bin=64, objective="reg:squarederror")
+    booster = gbdt.train(torch.from_numpy(X[lo:hi]).to(dev), torch.from_numpy(y[lo:hi]).to(dev), params=params) \
+        if hasattr(gbdt, "train") else None
+    if booster is None:
+        return None
+    pred = booster.predict(torch.from_numpy(X[:2000]).to(dev)).float().cpu()
+    sig = hvd.allgather(pred.double().sum().reshape(1))
+    return pred.tolist()[:50], bool((sig == sig[0]).all().item()), float(((pred - torch.from_numpy(y[:2000])) ** 2).mean())
