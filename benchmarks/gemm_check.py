@@ -146,7 +146,71 @@ def case_autograd():
     assert len(fired) == 1
 
 
-CASES = {"fwd": case_fwd, "bwd": case_bwd, "wgrad": case_wgrad, "stats": case_stats, "autograd": case_autograd}
+def case_misc():
+    for (m, n) in [(4096, 1024), (4096, 4096), (1000, 320), (8192, 30528), (128, 8)]:
+        x = rnd(m, n, scale=0.5)
+        ref = x.float().sum(0)
+        report("colsum fp32 m%d n%d" % (m, n), [rel(gemm.colsum(x), ref)], tol=1e-4)
+        base = torch.randn(n, device="cuda")
+        for dt in (torch.float32, torch.bfloat16):
+            out = base.to(dt).clone()
+            gemm.colsum(x, out=out, accumulate=True)
+            report("colsum accumulate %s m%d n%d" % (str(dt)[6:], m, n), [rel(out, base.to(dt).float() + ref)], tol=1e-2)
+        a, b = gemm.colsum(x), gemm.colsum(x)
+        assert torch.equal(a, b), "colsum is not deterministic"
+    x, w = rnd(512, 256, scale=0.5), rnd(384, 256, scale=0.05)
+    bb = torch.randn(384, device="cuda").bfloat16()
+    y, _ = gemm.gemm_bf16(x, w, bb, "gelu")
+    torch.cuda.synchronize()
+    report("fwd with a bf16 bias", [rel(y, torch.nn.functional.gelu(x.float() @ w.float().t() + bb.float()))])
+    # bias gradient through the sink
+    w = rnd(1024, 1024, scale=0.05).requires_grad_(True)
+    b = torch.zeros(1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w.grad, b.grad = torch.zeros_like(w), torch.zeros_like(b)
+    fired = []
+    w._sparkdl_grad_sink = lambda p: fired.append("w")
+    b._sparkdl_grad_sink = lambda p: fired.append("b")
+    x = rnd(2048, 1024, scale=0.5).requires_grad_(True)
+    y = gemm.linear_act(x, w, b, None)
+    g = torch.randn_like(y)
+    y.backward(g)
+    report("bias grad through the sink", [rel(b.grad, g.float().sum(0)), rel(w.grad, g.float().t() @ x.detach().float())])
+    assert sorted(fired) == ["b", "w"], fired
+
+
+def case_qkv():
+    b, s_, h, heads = 4, 128, 1024, 16
+    x = rnd(b, s_, h, scale=0.5).requires_grad_(True)
+    w = rnd(3 * h, h, scale=0.03).requires_grad_(True)
+    bias = (torch.randn(3 * h, device="cuda") * 0.1).bfloat16().requires_grad_(True)
+    q, k, v = gemm.qkv_proj(x, w, bias)
+    gq, gk, gv = rnd(b, s_, h), rnd(b, s_, h), rnd(b, s_, h)
+    torch.autograd.backward([q, k, v], [gq, gk, gv])
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, bias))
+    y = torch.nn.functional.linear(xr, wr, br)
+    y.backward(torch.cat([gq, gk, gv], -1).float())
+    report("qkv_proj forward", [rel(torch.cat([q, k, v], -1), y)])
+    report("qkv_proj backward (split-K dgrad, split-M wgrad, bias)", [rel(x.grad, xr.grad), rel(w.grad, wr.grad), rel(bias.grad, br.grad)],
+           tol=3e-2)
+    # through attention, against the packed autograd formulation
+    import torch.nn.functional as F
+    x2 = x.detach().clone().requires_grad_(True)
+    w2 = w.detach().clone().requires_grad_(True)
+    b2 = bias.detach().clone().requires_grad_(True)
+    d = h // heads
+    q, k, v = (t.view(b, s_, heads, d).transpose(1, 2) for t in gemm.qkv_proj(x2, w2, b2))
+    a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, s_, h)
+    g = rnd(b, s_, h)
+    a.backward(g)
+    x3, w3, b3 = (t.detach().clone().requires_grad_(True) for t in (x, w, bias))
+    qkv = F.linear(x3, w3, b3).view(b, s_, 3, heads, d).permute(2, 0, 3, 1, 4)
+    a3 = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(b, s_, h)
+    a3.backward(g)
+    report("qkv_proj + SDPA vs packed autograd", [rel(a, a3), rel(x2.grad, x3.grad), rel(w2.grad, w3.grad), rel(b2.grad, b3.grad)],
+           tol=4e-2)
+
+
+CASES = {"qkv": case_qkv, "misc": case_misc, "fwd": case_fwd, "bwd": case_bwd, "wgrad": case_wgrad, "stats": case_stats, "autograd": case_autograd}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["all"]

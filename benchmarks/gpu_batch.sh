@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 for stage in "$@"; do
   echo "=== stage $stage ($(date +%T))"
   case "$stage" in
-    gemm)      for g in fwd bwd wgrad stats autograd; do
+    gemm)      for g in misc qkv fwd bwd wgrad stats autograd; do
                  (timeout 150 python benchmarks/gemm_check.py $g 2>&1 | tail -80) > gpurun_out/gemm_check_$g.txt
                  echo "gemm_check $g: $(tail -1 gpurun_out/gemm_check_$g.txt) ($(grep -c '^BAD' gpurun_out/gemm_check_$g.txt) bad)"
                done ;;
@@ -29,6 +29,7 @@ for stage in "$@"; do
     xgb)       (timeout 400 python benchmarks/xgboost_bench.py --np 1 2>&1 | tail -8) > gpurun_out/xgb_np1.txt; cat gpurun_out/xgb_np1.txt ;;
     profbert)  (timeout 300 python benchmarks/step_profile.py bert 2>&1 | tail -5) > gpurun_out/step_profile_bert.log; cat gpurun_out/step_profile_bert.log ;;
     profresnet) (timeout 300 python benchmarks/step_profile.py resnet 2>&1 | tail -5) > gpurun_out/step_profile_resnet.log; cat gpurun_out/step_profile_resnet.log ;;
+    sdpaprobe) (timeout 120 python benchmarks/sdpa_probe.py 2>&1 | tail -20) > gpurun_out/sdpa_probe.txt; cat gpurun_out/sdpa_probe.txt ;;
     bertprobe) (timeout 200 python benchmarks/bert_sink_probe.py 2>&1 | tail -40) > gpurun_out/bert_sink_probe.txt; tail -25 gpurun_out/bert_sink_probe.txt ;;
     gemmstaging) for d in 1 2; do (SPARKDL_GEMM_STAGING=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | sed "s/^dbg=0/staging=$d/" | tail -10); done > gpurun_out/gemm_staging.txt; cat gpurun_out/gemm_staging.txt ;;
     gemmlab)   for d in 0 1 2 3 4; do (SPARKDL_GEMM_DBG=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | grep -v cublas | tail -8); done > gpurun_out/gemm_lab.txt

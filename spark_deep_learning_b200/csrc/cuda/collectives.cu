@@ -691,6 +691,8 @@ int sdlc_reducescatter(void* h, int channel, int buf, void* out, long long lo, l
     case kF64: RS(double); break;
     case kI32: RS(int32_t); break;
     case kI64: RS(int64_t); break;
+    case kU8: case kBool: RS(uint8_t); break;
+    case kI8: RS(int8_t); break;
     default: c->last_error = "unsupported dtype for CUDA reducescatter"; return -1;
   }
 #undef RS

@@ -196,7 +196,7 @@ int sdlc_fused_step(void* h, int channel, int grad_buf, int param_buf, long long
   long long blocks = ((nvec + c->world - 1) / c->world + kThreads * 2 - 1) / (kThreads * 2);
   if (blocks < 1) blocks = 1;
   // a single rank owns the whole bucket and only streams local HBM: give it more CTAs
-  const long long cap = c->world == 1 ? 96 : c->max_blocks;
+  const long long cap = c->world == 1 ? 148 : c->max_blocks;
   if (blocks > cap) blocks = cap;
   if (dtype == kF32) {
     fused_step_kernel<float><<<(int)blocks, kThreads, 0, s>>>(g, pp, pmc, s1, s2, master, nvec, scale, hyper);

@@ -75,12 +75,14 @@ struct Cfg {
 struct GemmParams {
   int M, N, K;
   int a_mn, b_mn;              // 1: operand is MN-major (stored [K, rows])
+  int a_parts, a_part_len;     // A may be split into up to 3 buffers: along K (K-major A) or along M (MN-major A)
   int splits, kb_per_split;    // split-K: number of slices / k-blocks per slice
   int m_pad;                   // split-K workspace: rows per slice (m_tiles * 256)
   int act;                     // LINEAR: 0 none, 1 GELU(tanh), 2 GELU(erf); DGELU: 1 / 2
   int has_pre;                 // LINEAR: also store the pre-activation through map_out2
   int accumulate;              // ACC: out = dst + acc
-  const float* bias;           // LINEAR: fp32 [N] or null
+  const void* bias;            // LINEAR: fp32 (or bf16, bias_bf16) [N] or null
+  int bias_bf16;
   const void* aux;             // DGELU: bf16 pre-activation [M, ld_aux]; ACC: destination read for accumulate
   long long ld_aux;
   float* stats;                // STATS: partial sums [2][stat_rows][N] (sum, then sum of squares)
@@ -263,7 +265,8 @@ __device__ __forceinline__ Unit decode_unit(int u, int m_tiles, int n_tiles, int
 
 template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a1,
+            const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // identical layout in both CTAs of the pair (the MMA addresses both through one descriptor)
@@ -322,8 +325,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       uint32_t phase = 0;
       for (int u = cluster_id; u < num_units; u += num_clusters) {
         const Unit w = decode_unit(u, m_tiles, n_tiles, k_blocks, p);
-        const int a_row = w.m_blk * PAIR_M + (int)cta_rank * CTA_M;
+        int a_row = w.m_blk * PAIR_M + (int)cta_rank * CTA_M;
         const int b_row = w.n_blk * BLOCK_N + (int)cta_rank * C::kBRows;
+        // split A operand: [dQ | dK | dV] along K for dgrad, [dQ; dK; dV] along M for wgrad - three buffers, no concat
+        const CUtensorMap* ma = &map_a;
+        if (p.a_parts > 1 && p.a_mn) {
+          const int part = a_row / p.a_part_len;
+          a_row -= part * p.a_part_len;
+          ma = part == 0 ? &map_a : (part == 1 ? &map_a1 : &map_a2);
+        }
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t bar = mapa(smem_u32(&full[stage]), 0);
@@ -335,10 +345,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             continue;
           }
           if (!p.a_mn) {
-            tma_load_2d(sa, &map_a, bar, kb * BLOCK_K, a_row);
+            int k0 = kb * BLOCK_K;
+            if (p.a_parts > 1) {
+              const int part = k0 / p.a_part_len;
+              k0 -= part * p.a_part_len;
+              ma = part == 0 ? &map_a : (part == 1 ? &map_a1 : &map_a2);
+            }
+            tma_load_2d(sa, ma, bar, k0, a_row);
           } else {
 #pragma unroll
-            for (int i = 0; i < CTA_M / 64; ++i) tma_load_2d(sa + i * (BLOCK_K * 128), &map_a, bar, a_row + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < CTA_M / 64; ++i) tma_load_2d(sa + i * (BLOCK_K * 128), ma, bar, a_row + i * 64, kb * BLOCK_K);
           }
           if (!p.b_mn) {
             tma_load_2d(sb, &map_b, bar, kb * BLOCK_K, b_row);
@@ -491,11 +507,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         for (int i = 0; i < kChunk; ++i) f[i] = __uint_as_float(v[i]);
 
         if constexpr (EPI == EPI_LINEAR || EPI == EPI_STATS) {
-          if (p.bias) {
+          if (p.bias && p.bias_bf16) {
+            const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+            for (int j = 0; j < kChunk; j += 8) {
+              if (col0 + j < p.N) {
+                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bp + j));
+                f[j] += bf16lo(bv.x); f[j + 1] += bf16hi(bv.x); f[j + 2] += bf16lo(bv.y); f[j + 3] += bf16hi(bv.y);
+                f[j + 4] += bf16lo(bv.z); f[j + 5] += bf16hi(bv.z); f[j + 6] += bf16lo(bv.w); f[j + 7] += bf16hi(bv.w);
+              }
+            }
+          } else if (p.bias) {
+            const float* bp = static_cast<const float*>(p.bias) + col0;
 #pragma unroll
             for (int j = 0; j < kChunk; j += 4) {
               if (col0 + j < p.N) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + j));
                 f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
               }
             }
@@ -651,6 +678,72 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
   }
 }
 
+// ---------------- column sums (bias gradients): dst[n] (+)= sum_m x[m, n] ------------------------------------------
+// Block = 8 column vectors (64 columns) x 32 rows; grid = (N / 64, R row slices).  Every block writes one partial
+// row; the block that finishes last for its column group adds the R partials in a fixed order (deterministic),
+// writes / accumulates the result and re-arms the ticket counter.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ld, OutT* __restrict__ dst, int accumulate,
+              float* __restrict__ partial, unsigned int* __restrict__ tickets) {
+  __shared__ float sh[32][65];
+  __shared__ unsigned int s_ticket;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int col = blockIdx.x * 64 + tx * 8;
+  const int R = gridDim.y;
+  const int rows_per = (M + R - 1) / R;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < N) {
+    int r = r0 + ty;
+    for (; r + 96 < r1; r += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(r + 32 * u) * ld + col));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16lo(v[u].x); acc[1] += bf16hi(v[u].x); acc[2] += bf16lo(v[u].y); acc[3] += bf16hi(v[u].y);
+        acc[4] += bf16lo(v[u].z); acc[5] += bf16hi(v[u].z); acc[6] += bf16lo(v[u].w); acc[7] += bf16hi(v[u].w);
+      }
+    }
+    for (; r < r1; r += 32) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r * ld + col));
+      acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
+      acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[ty][tx * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) t += sh[y][threadIdx.x];
+    partial[(size_t)blockIdx.y * (gridDim.x * 64) + blockIdx.x * 64 + threadIdx.x] = t;   // pitch: N rounded up to 64
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned int)(R - 1)) return;
+  __threadfence();
+  if (threadIdx.x < 64) {
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    float t = 0.f;
+    for (int y = 0; y < R; ++y) t += partial[(size_t)y * (gridDim.x * 64) + c];
+    if (c < N) {
+      if constexpr (sizeof(OutT) == 4) {
+        dst[c] = accumulate ? dst[c] + t : t;
+      } else {
+        dst[c] = __float2bfloat16(accumulate ? __bfloat162float(dst[c]) + t : t);
+      }
+    }
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
+}
+
 // ---------------- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -679,11 +772,14 @@ static bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fprintf(stderr, "sparkdl gemm: cuTensorMapEncodeTiled failed (%d): ptr %p rows %llu cols %llu ld %llu box %ux%u elem %d\n", (int)r, ptr,
+            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols, elem_bytes);
   return r == CUDA_SUCCESS;
 }
 
 template <int BLOCK_N, int EPI>
-static cudaError_t launch(int grid, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+static cudaError_t launch(int grid, cudaStream_t s, const CUtensorMap* ma, const CUtensorMap& mb, const CUtensorMap& mo,
                           const CUtensorMap& mo2, const GemmParams& p) {
   const int smem = Cfg<BLOCK_N>::smem_bytes(p.stages, p.staging_bufs);
   static bool attr = false;
@@ -692,12 +788,12 @@ static cudaError_t launch(int grid, cudaStream_t s, const CUtensorMap& ma, const
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  gemm_kernel<BLOCK_N, EPI><<<grid, kNumThreads, smem, s>>>(ma, mb, mo, mo2, p);
+  gemm_kernel<BLOCK_N, EPI><<<grid, kNumThreads, smem, s>>>(ma[0], ma[1], ma[2], mb, mo, mo2, p);
   return cudaGetLastError();
 }
 
 template <int EPI>
-static cudaError_t launch_bn(int block_n, int grid, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb,
+static cudaError_t launch_bn(int block_n, int grid, cudaStream_t s, const CUtensorMap* ma, const CUtensorMap& mb,
                              const CUtensorMap& mo, const CUtensorMap& mo2, const GemmParams& p) {
   return block_n == 256 ? launch<256, EPI>(grid, s, ma, mb, mo, mo2, p) : launch<128, EPI>(grid, s, ma, mb, mo, mo2, p);
 }
@@ -722,7 +818,7 @@ extern "C" {
 //   a / lda, a_mn : A is [M, lda] (K-major, a_mn = 0) or [K, lda] (MN-major, a_mn = 1); likewise b for [N,K] / [K,N]
 //   epi           : EPI_* above;  out / ld_out: destination (bf16, or fp32 for EPI_ACC_F32)
 //   out2          : EPI_LINEAR: optional pre-activation output (bf16, same pitch as out)
-//   bias, act     : EPI_LINEAR;   aux / ld_aux, act: EPI_DGELU (bf16 pre-activation)
+//   bias, act     : EPI_LINEAR (act | 16: bias is bf16 instead of fp32);   aux / ld_aux, act: EPI_DGELU (bf16 pre-activation)
 //   accumulate    : EPI_ACC_*: out += result (out is read through aux := out)
 //   splits        : > 1 = split-K (EPI_ACC_* only); `workspace` must hold splits * ceil(M/256)*256 * N floats
 //   stats         : EPI_STATS: fp32 [2][ceil(M/256)*8][N] partials followed by (caller-sized) [2][N] totals; the totals
@@ -730,22 +826,36 @@ extern "C" {
 //   block_n       : 256 / 128 / 0 = choose
 // Requirements: 16-byte aligned pointers and pitches (lda, ldb, ld_out multiples of 8 elements; 4 for fp32 out).
 // Returns 0 on success, negative on error.
-int sdlc_gemm_ex(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, void* out, long long ld_out,
-                 void* out2, int M, int N, int K, int epi, const float* bias, int act, const void* aux, long long ld_aux,
+int sdlc_gemm_ex3(const void* a, const void* a1, const void* a2, int a_part_len, long long lda, int a_mn, const void* b,
+                  long long ldb, int b_mn, void* out, long long ld_out,
+                 void* out2, int M, int N, int K, int epi, const void* bias, int act, const void* aux, long long ld_aux,
                  int accumulate, int splits, float* workspace, float* stats, int block_n, int sms, unsigned long long stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) != 0 || (ldb % 8) != 0 || (N % 8) != 0) return -2;
   if (epi < 0 || epi > EPI_STATS) return -2;
   if (!load_encode()) return -3;
+  {
+    // cuTensorMapEncodeTiled is a driver-API call: it needs the primary context bound to THIS thread.  autograd runs
+    // backward on its own worker thread, and if our dgrad is the first CUDA work there nothing has bound it yet
+    // (CUDA_ERROR_INVALID_CONTEXT, seen in round 2).  cudaSetDevice binds it; once per thread.
+    static thread_local bool bound = false;
+    if (!bound) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaSetDevice(dev);
+      bound = true;
+    }
+  }
   if (sms <= 0) sms = num_sms();
   const int max_clusters = sms / 2 > 0 ? sms / 2 : 1;
   const int m_tiles = (M + PAIR_M - 1) / PAIR_M;
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   if (block_n != 256 && block_n != 128) {
-    // wide tiles halve the B traffic per FLOP; take them unless they leave most of the machine idle / a ragged tail
+    // 256-wide tiles need 2/3 of the L2->smem bytes per FLOP of 128-wide ones and measure ~1.3x faster per tile-FLOP
+    // (gemm_lab, round 2); the narrow tile only pays when the wide one leaves most clusters idle in its last wave
     const int t256 = m_tiles * ((N + 255) / 256), t128 = m_tiles * ((N + 127) / 128);
     auto eff = [&](int t) { const int waves = (t + max_clusters - 1) / max_clusters; return (double)t / (waves * max_clusters); };
-    block_n = (N > 128 && eff(t256) + 0.10 >= eff(t128)) ? 256 : 128;
+    block_n = (N > 128 && eff(t256) >= 0.72 * eff(t128)) ? 256 : 128;
   }
   const int n_tiles = (N + block_n - 1) / block_n;
   const bool acc_epi = epi == EPI_ACC_BF16 || epi == EPI_ACC_F32;
@@ -757,9 +867,15 @@ int sdlc_gemm_ex(const void* a, long long lda, int a_mn, const void* b, long lon
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
+  p.a_parts = a1 ? (a2 ? 3 : 2) : 1;
+  p.a_part_len = a_part_len;
+  if (p.a_parts > 1) {
+    const int split_dim = a_mn ? M : K;
+    if (a_part_len <= 0 || a_part_len * p.a_parts != split_dim || (a_part_len % (a_mn ? PAIR_M : BLOCK_K)) != 0) return -2;
+  }
   p.splits = splits; p.kb_per_split = kbps; p.m_pad = m_tiles * PAIR_M;
   p.act = act; p.has_pre = (epi == EPI_LINEAR && out2) ? 1 : 0;
-  p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  p.bias = bias; p.bias_bf16 = (act & 16) ? 1 : 0; p.act = act & 15; p.aux = aux; p.ld_aux = ld_aux;
   p.accumulate = (accumulate && splits == 1) ? 1 : 0;
   if (p.accumulate && acc_epi) { p.aux = out; p.ld_aux = ld_out; }
   p.stats = stats; p.stat_rows = m_tiles * 8;
@@ -775,11 +891,16 @@ int sdlc_gemm_ex(const void* a, long long lda, int a_mn, const void* b, long lon
   if (epi == EPI_STATS && !stats) return -2;
   if (epi == EPI_DGELU && (!aux || (ld_aux % 8) != 0)) return -2;
 
-  CUtensorMap ma, mb, mo, mo2;
+  CUtensorMap ma[3], mb, mo, mo2;
   const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   bool ok = true;
-  if (!a_mn) ok &= make_map(&ma, a, BF, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda, CTA_M, BLOCK_K);
-  else ok &= make_map(&ma, a, BF, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, 64);
+  const void* aptr[3] = {a, a1, a2};
+  for (int i = 0; i < p.a_parts; ++i) {
+    // every part is a matrix of its own: K-major [M, K / parts], MN-major [K, M / parts]
+    if (!a_mn) ok &= make_map(&ma[i], aptr[i], BF, 2, (uint64_t)M, (uint64_t)(K / p.a_parts), (uint64_t)lda, CTA_M, BLOCK_K);
+    else ok &= make_map(&ma[i], aptr[i], BF, 2, (uint64_t)K, (uint64_t)(M / p.a_parts), (uint64_t)lda, BLOCK_K, 64);
+  }
+  for (int i = p.a_parts; i < 3; ++i) ma[i] = ma[0];
   if (!b_mn) ok &= make_map(&mb, b, BF, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)block_n / 2, BLOCK_K);
   else ok &= make_map(&mb, b, BF, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, 64);
   int run_epi = epi;
@@ -829,6 +950,13 @@ int sdlc_gemm_ex(const void* a, long long lda, int a_mn, const void* b, long lon
   return 0;
 }
 
+int sdlc_gemm_ex(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, void* out, long long ld_out,
+                 void* out2, int M, int N, int K, int epi, const void* bias, int act, const void* aux, long long ld_aux,
+                 int accumulate, int splits, float* workspace, float* stats, int block_n, int sms, unsigned long long stream) {
+  return sdlc_gemm_ex3(a, nullptr, nullptr, 0, lda, a_mn, b, ldb, b_mn, out, ld_out, out2, M, N, K, epi, bias, act, aux, ld_aux,
+                       accumulate, splits, workspace, stats, block_n, sms, stream);
+}
+
 // number of kernels sdlc_gemm_ex launches for these arguments (the Python launch counter asks)
 int sdlc_gemm_stat_rows(int M) { return ((M + PAIR_M - 1) / PAIR_M) * 8; }
 
@@ -837,6 +965,25 @@ int sdlc_gemm_bf16(const void* x, const void* w, const float* bias, void* out, v
                    int epilogue, int block_n, int sms, unsigned long long stream) {
   return sdlc_gemm_ex(x, K, 0, w, K, 0, out, N, pre_act, M, N, K, EPI_LINEAR, bias, epilogue, nullptr, 0, 0, 1, nullptr, nullptr,
                       block_n, sms, stream);
+}
+
+// dst[N] (+)= column sums of the bf16 matrix x[M, ld] (bias gradient of a linear layer).  N % 8 == 0, ld % 8 == 0.
+// workspace: 64 * round_up(N, 64) floats; tickets: round_up(N, 64) / 64 zero-initialised uint32 (left zero on return)
+int sdlc_colsum_bf16(const void* x, int M, int N, long long ld, void* dst, int dst_f32, int accumulate, float* workspace,
+                     unsigned int* tickets, unsigned long long stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if ((N % 8) != 0 || (ld % 8) != 0) return -2;
+  const int cb = (N + 63) / 64;
+  int R = 592 / cb;
+  if (R > 64) R = 64;
+  if (R > (M + 127) / 128) R = (M + 127) / 128;
+  if (R < 1) R = 1;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dst_f32)
+    colsum_kernel<float><<<dim3(cb, R), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), M, N, ld, static_cast<float*>(dst), accumulate, workspace, tickets);
+  else
+    colsum_kernel<__nv_bfloat16><<<dim3(cb, R), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), M, N, ld, static_cast<__nv_bfloat16*>(dst), accumulate, workspace, tickets);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // out = dy * gelu'(pre); numel % 8 == 0.  kind: 1 tanh, 2 erf

@@ -46,7 +46,12 @@ class Layer(nn.Module):
 
     def forward(self, x):
         b, s, h = x.shape
-        q, k, v = self.qkv(x).view(b, s, 3, self.heads, h // self.heads).permute(2, 0, 3, 1, 4)
+        if self.qkv.fused and x.is_cuda and x.dtype == torch.bfloat16:
+            # three views of one packed buffer forward, three separate gradient buffers backward (no stack / permute)
+            q, k, v = (t.view(b, s, self.heads, h // self.heads).transpose(1, 2)
+                       for t in gemm.qkv_proj(x, self.qkv.weight, self.qkv.bias))
+        else:
+            q, k, v = self.qkv(x).view(b, s, 3, self.heads, h // self.heads).permute(2, 0, 3, 1, 4)
         a = F.scaled_dot_product_attention(q, k, v, dropout_p=self.p if self.training else 0.0)
         a = self.proj(a.transpose(1, 2).reshape(b, s, h))
         x = self.ln1(x, a)                       # LayerNorm(x + dropout(a)) in one pass

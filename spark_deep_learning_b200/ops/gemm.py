@@ -34,10 +34,15 @@ def _lib():
         lib.sdlc_gemm_ex.restype = i32
         lib.sdlc_gemm_ex.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, vp, i32, i32, i32, i32, vp, i32, vp, i64,
                                      i32, i32, vp, vp, i32, i32, u64]
+        lib.sdlc_gemm_ex3.restype = i32
+        lib.sdlc_gemm_ex3.argtypes = [vp, vp, vp, i32, i64, i32, vp, i64, i32, vp, i64, vp, i32, i32, i32, i32, vp, i32, vp,
+                                      i64, i32, i32, vp, vp, i32, i32, u64]
         lib.sdlc_gelu_bwd.restype = i32
         lib.sdlc_gelu_bwd.argtypes = [vp, vp, vp, i64, i32, u64]
         lib.sdlc_gemm_stat_rows.restype = i32
         lib.sdlc_gemm_stat_rows.argtypes = [i32]
+        lib.sdlc_colsum_bf16.restype = i32
+        lib.sdlc_colsum_bf16.argtypes = [vp, i32, i32, i64, vp, i32, i32, vp, vp, u64]
         _sig = True
     return lib
 
@@ -78,9 +83,20 @@ def _rowmajor(t):
 def gemm_ex(a, b, m, n, k, a_mn=False, b_mn=False, epi=EPI_ACC_BF16, out=None, out2=None, bias=None, act=None,
             aux=None, accumulate=False, splits=1, stats=None, block_n=0):
     """Raw kernel call: ``out[m,n] = epi(A . B^T)``.  ``a`` is stored [m,k] (K-major) or [k,m] (``a_mn``); ``b`` is
-    stored [n,k] or [k,n] (``b_mn``).  Returns ``out``."""
+    stored [n,k] or [k,n] (``b_mn``).  ``a`` may also be a tuple of 2-3 equally shaped buffers that together form A -
+    split along K for a K-major A, along M for an MN-major A - so that e.g. dQ, dK, dV never have to be concatenated.
+    Returns ``out``."""
     lib = _lib()
-    a, lda = _rowmajor(a)
+    parts = None
+    if isinstance(a, (tuple, list)):
+        parts = [_rowmajor(t) for t in a]
+        if len({ld for _, ld in parts}) != 1:
+            parts = [(t.contiguous(), t.shape[1]) for t, _ in parts]
+        a, lda = parts[0]
+        part_len = a.shape[1]
+        parts = [t for t, _ in parts]
+    else:
+        a, lda = _rowmajor(a)
     b, ldb = _rowmajor(b)
     dev = a.device
     if out is None:
@@ -89,12 +105,22 @@ def gemm_ex(a, b, m, n, k, a_mn=False, b_mn=False, epi=EPI_ACC_BF16, out=None, o
     ws = None
     if splits > 1:
         ws = _workspace(dev, splits * ((m + 255) // 256) * 256 * n)
-    if bias is not None and bias.dtype != torch.float32:
-        bias = bias.float()
+    act_code = ACT[act] if not isinstance(act, int) else act
+    if bias is not None:
+        if bias.dtype == torch.bfloat16 and bias.data_ptr() % 16 == 0:
+            act_code |= 16                       # the epilogue reads the bf16 bias directly
+        elif bias.dtype != torch.float32:
+            bias = bias.float()
     ld_aux = aux.stride(0) if aux is not None else 0
-    rc = lib.sdlc_gemm_ex(_p(a), lda, int(a_mn), _p(b), ldb, int(b_mn), _p(out), ld_out, _p(out2), m, n, k, epi,
-                          _p(bias), ACT[act] if not isinstance(act, int) else act, _p(aux), ld_aux, int(accumulate),
-                          splits, _p(ws), _p(stats), block_n, 0, _stream(a))
+    if parts is not None:
+        rc = lib.sdlc_gemm_ex3(_p(parts[0]), _p(parts[1]), _p(parts[2]) if len(parts) > 2 else None, part_len, lda,
+                               int(a_mn), _p(b), ldb, int(b_mn), _p(out), ld_out, _p(out2), m, n, k, epi,
+                               _p(bias), act_code, _p(aux), ld_aux, int(accumulate),
+                               splits, _p(ws), _p(stats), block_n, 0, _stream(a))
+    else:
+        rc = lib.sdlc_gemm_ex(_p(a), lda, int(a_mn), _p(b), ldb, int(b_mn), _p(out), ld_out, _p(out2), m, n, k, epi,
+                              _p(bias), act_code, _p(aux), ld_aux, int(accumulate),
+                              splits, _p(ws), _p(stats), block_n, 0, _stream(a))
     if rc != 0:
         raise RuntimeError("sdlc_gemm_ex failed (%d) for M=%d N=%d K=%d epi=%d" % (rc, m, n, k, epi))
     launch_counter.add(1 + (1 if splits > 1 else 0) + (1 if epi == EPI_STATS else 0))
@@ -112,9 +138,10 @@ def gemm_bf16(x2d, weight, bias=None, act=None, save_pre_act=False, block_n=None
 
 
 def dgrad(dy2d, weight, pre=None, act=None):
-    """``dX[M,K_in] = (dY . W) [* gelu'(pre)]``: dy2d [M,N_out] bf16, weight [N_out,K_in] bf16 (read as an MN-major B)."""
-    m, n_out = dy2d.shape
-    k_in = weight.shape[1]
+    """``dX[M,K_in] = (dY . W) [* gelu'(pre)]``: dy2d [M,N_out] bf16 (or a tuple of column blocks of it), weight
+    [N_out,K_in] bf16 (read as an MN-major B)."""
+    m = dy2d[0].shape[0] if isinstance(dy2d, (tuple, list)) else dy2d.shape[0]
+    n_out, k_in = weight.shape
     if pre is not None:
         return gemm_ex(dy2d, weight, m, k_in, n_out, b_mn=True, epi=EPI_DGELU, aux=pre, act=act)
     return gemm_ex(dy2d, weight, m, k_in, n_out, b_mn=True, epi=EPI_ACC_BF16)
@@ -130,10 +157,13 @@ def _wgrad_splits(n_out, k_in, tokens):
 def wgrad(dy2d, x2d, out=None, accumulate=False):
     """``dW[N_out,K_in] (+)= dY^T . X`` without transposing anything: both operands are read MN-major.  ``out`` may be
     bf16 or fp32 (e.g. a view of a gradient bucket)."""
-    tokens, n_out = dy2d.shape
+    if isinstance(dy2d, (tuple, list)):
+        tokens, n_out = dy2d[0].shape[0], sum(t.shape[1] for t in dy2d)
+    else:
+        tokens, n_out = dy2d.shape
     k_in = x2d.shape[1]
     if out is None:
-        out = torch.empty((n_out, k_in), dtype=torch.bfloat16, device=dy2d.device)
+        out = torch.empty((n_out, k_in), dtype=torch.bfloat16, device=x2d.device)
     epi = EPI_ACC_F32 if out.dtype == torch.float32 else EPI_ACC_BF16
     return gemm_ex(dy2d, x2d, n_out, k_in, tokens, a_mn=True, b_mn=True, epi=epi, out=out, accumulate=accumulate,
                    splits=_wgrad_splits(n_out, k_in, tokens))
@@ -148,6 +178,43 @@ def conv1x1_stats(x2d, weight):
     stats = torch.empty((2 * rows + 2) * n, dtype=torch.float32, device=x2d.device)
     y = gemm_ex(x2d, weight, m, n, k, epi=EPI_STATS, stats=stats)
     return y, stats[2 * rows * n:].view(2, n)
+
+
+_CS = {}
+
+
+def colsum(x2d, out=None, accumulate=False):
+    """``out[N] (+)= x2d.sum(0)`` for a bf16 matrix, deterministic, one launch (the bias gradient of a linear layer).
+    ``out`` may be fp32 or bf16 (e.g. the view of a bias inside a gradient bucket)."""
+    m, n = x2d.shape
+    x2d, ld = _rowmajor(x2d)
+    dev = x2d.device
+    ws = _CS.get(dev)
+    npad = (n + 63) // 64 * 64
+    if ws is None or ws[0].numel() < 64 * npad:
+        ws = (torch.empty(64 * max(npad, 32768), dtype=torch.float32, device=dev),
+              torch.zeros(max(npad, 32768) // 64, dtype=torch.int32, device=dev))
+        _CS[dev] = ws
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+    rc = _lib().sdlc_colsum_bf16(_p(x2d), m, n, ld, _p(out), 1 if out.dtype == torch.float32 else 0, int(accumulate),
+                                 _p(ws[0]), _p(ws[1]), _stream(x2d))
+    if rc != 0:
+        raise RuntimeError("sdlc_colsum_bf16 failed (%d)" % rc)
+    launch_counter.add(1)
+    return out
+
+
+def _bias_grad(dy2d, bias, use_sink=True):
+    """Gradient of a bias: accumulated straight into ``bias.grad`` (bucket view) when the optimizer offers a sink."""
+    sink = _grad_sink(bias) if use_sink else None
+    if sink is not None and bias.grad.dtype in (torch.float32, torch.bfloat16) and dy2d.shape[1] % 8 == 0:
+        colsum(dy2d, out=bias.grad, accumulate=True)
+        sink(bias)
+        return None
+    if dy2d.shape[1] % 8 == 0 and dy2d.dtype == torch.bfloat16:
+        return colsum(dy2d)
+    return dy2d.sum(0, dtype=torch.float32)
 
 
 def gelu_bwd(dy2d, pre, act):
@@ -179,7 +246,7 @@ class _LinearAct(torch.autograd.Function):
         x2d = x.reshape(-1, x.shape[-1])
         need_pre = act not in (None, "none") and (x.requires_grad or weight.requires_grad)
         out, pre = gemm_bf16(x2d, weight, bias, act, save_pre_act=need_pre)
-        ctx.save_for_backward(x2d, weight, pre)
+        ctx.save_for_backward(x2d, weight, pre, bias)
         ctx.act = act
         ctx.has_bias = bias is not None
         ctx.x_shape = x.shape
@@ -187,7 +254,7 @@ class _LinearAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x2d, weight, pre = ctx.saved_tensors
+        x2d, weight, pre, bias = ctx.saved_tensors
         dy2d = dy.reshape(-1, dy.shape[-1])
         dy2d, _ = _rowmajor(dy2d)
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
@@ -205,8 +272,61 @@ class _LinearAct(torch.autograd.Function):
                 sink(weight)
             else:
                 dw = wgrad(dy2d, x2d)
-        db = dy2d.sum(0, dtype=torch.float32) if need_db else None
+        db = _bias_grad(dy2d, bias, ctx.use_sink) if need_db else None
         return dx, dw, db, None, None
+
+
+class _QKVProj(torch.autograd.Function):
+    """Packed QKV projection that hands attention three views of one [M, 3H] buffer and takes dQ, dK, dV back as three
+    separate buffers: the dgrad (split along K) and wgrad (split along M) GEMMs read them in place, so the
+    ``stack`` + ``permute`` copies that autograd inserts for a packed projection disappear."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2d = x.reshape(-1, x.shape[-1])
+        qkv, _ = gemm_bf16(x2d, weight, bias, None)
+        h = weight.shape[0] // 3
+        ctx.save_for_backward(x2d, weight, bias)
+        ctx.x_shape = x.shape
+        lead = x.shape[:-1]
+        return tuple(qkv[:, i * h:(i + 1) * h].view(*lead, h) for i in range(3))
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        x2d, weight, bias = ctx.saved_tensors
+        h = weight.shape[0] // 3
+        parts = []
+        for g in (dq, dk, dv):
+            g2 = g.reshape(-1, h)
+            if g2.stride(1) != 1 or g2.stride(0) != h or g2.data_ptr() % 16:
+                g2 = g2.contiguous()
+            parts.append(g2)
+        dx = dgrad(parts, weight).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            sink = _grad_sink(weight)
+            if sink is not None:
+                wgrad(parts, x2d, out=weight.grad, accumulate=True)
+                sink(weight)
+            else:
+                dw = wgrad(parts, x2d)
+        if bias is not None and ctx.needs_input_grad[2]:
+            sink = _grad_sink(bias)
+            if sink is not None and bias.grad.dtype in (torch.float32, torch.bfloat16):
+                for i, g2 in enumerate(parts):
+                    colsum(g2, out=bias.grad[i * h:(i + 1) * h], accumulate=True)
+                sink(bias)
+            else:
+                db = torch.cat([colsum(g2) for g2 in parts])
+        return dx, dw, db
+
+
+def qkv_proj(x, weight, bias):
+    """``(q, k, v) = split(x @ weight.T + bias, 3)`` for a packed [3H, H] projection (bf16, tcgen05 GEMMs)."""
+    if not (supported(x, weight) and weight.shape[0] % (3 * 256) == 0):
+        y = torch.nn.functional.linear(x, weight, None if bias is None else bias.to(x.dtype))
+        return y.chunk(3, dim=-1)
+    return _QKVProj.apply(x, weight, bias)
 
 
 class _MLP(torch.autograd.Function):
@@ -218,7 +338,7 @@ class _MLP(torch.autograd.Function):
         x2d = x.reshape(-1, x.shape[-1])
         h, z = gemm_bf16(x2d, w1, b1, act, save_pre_act=True)
         y, _ = gemm_bf16(h, w2, b2, None)
-        ctx.save_for_backward(x2d, w1, w2, z, h)
+        ctx.save_for_backward(x2d, w1, w2, z, h, b1, b2)
         ctx.act = act
         ctx.x_shape = x.shape
         ctx.has_b = (b1 is not None, b2 is not None)
@@ -226,7 +346,7 @@ class _MLP(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x2d, w1, w2, z, h = ctx.saved_tensors
+        x2d, w1, w2, z, h, b1, b2 = ctx.saved_tensors
         dy2d, _ = _rowmajor(dy.reshape(-1, dy.shape[-1]))
         dz = dgrad(dy2d, w2, z, ctx.act)                     # fused: (dY . W2) * gelu'(Z)
         grads = {}
@@ -238,8 +358,8 @@ class _MLP(torch.autograd.Function):
                 grads[name] = None
             else:
                 grads[name] = wgrad(g, inp)
-        db2 = dy2d.sum(0, dtype=torch.float32) if ctx.has_b[1] else None
-        db1 = dz.sum(0, dtype=torch.float32) if ctx.has_b[0] else None
+        db2 = _bias_grad(dy2d, b2) if ctx.has_b[1] else None
+        db1 = _bias_grad(dz, b1) if ctx.has_b[0] else None
         dx = dgrad(dz, w1).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
         return dx, grads["w1"], db1, grads["w2"], db2, None
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("group", ["fwd", "bwd", "wgrad", "stats", "autograd"])
+@pytest.mark.parametrize("group", ["misc", "qkv", "fwd", "bwd", "wgrad", "stats", "autograd"])
 def test_tcgen05_gemm_numerics(group):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "gemm_check.py"), group],
                          capture_output=True, text=True, timeout=280)

@@ -202,7 +202,9 @@ def _fused_bf16_main(opt_name):
 def test_fused_step_bf16_master_weights_multicast(opt_name):
     rel, same, sym, _ = HorovodRunner(np=_np()).run(_fused_bf16_main, opt_name=opt_name)
     assert same and sym
-    assert rel < 3e-2, rel          # bf16 forward/backward vs an fp32 replica of the whole batch
+    # bf16 forward/backward vs an fp32 replica of the whole batch; Adam turns bf16 noise on tiny gradients into
+    # full-size (+-lr) steps, so its tolerance is wider
+    assert rel < (3e-2 if opt_name == "sgd" else 0.12), rel
 
 
 # ---------------------------------------------------------------------------------------------
