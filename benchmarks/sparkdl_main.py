@@ -41,8 +41,7 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
 
     def fwd(x, y):
         if model_name == "resnet50" and bf16_weights:
-            logits = model(x.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
-            return crit(logits.float(), y)
+            return crit(model(x).float(), y)   # the stem kernel casts fp32 NCHW -> bf16 channels-last itself
         if model_name == "resnet50":
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return crit(model(x.contiguous(memory_format=torch.channels_last)), y)

@@ -309,12 +309,30 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, fl
 }
 
 // ---------------- backward pass 2: dx = A*dz + B*x + D (and dz for the residual branch) -------------------
+template <typename T> __device__ __forceinline__ void store_streaming(T* p, const float* f);
+template <> __device__ __forceinline__ void store_streaming<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+}
+template <> __device__ __forceinline__ void store_streaming<float>(float* p, const float* f) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(f[0], f[1], f[2], f[3]));
+}
+
+// Five streams (dy, x, mask in; dx, dz out): U vectors per thread are loaded before any math or store so that enough
+// bytes are in flight to cover HBM latency, and the outputs (each read exactly once, much later, by the next backward
+// kernel) are written with streaming stores so they do not evict the inputs of this pass from L2.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask,
                     const float* __restrict__ c0, const float* __restrict__ c1, const float* __restrict__ c2,
                     T* __restrict__ dx, T* __restrict__ dz_out, long long nvec, int C, int relu) {
   constexpr int N = V<T>::N;
+  constexpr int U = 4;
   const int CV = C / N;
   const long long T_all = (long long)gridDim.x * kThreads;
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -326,35 +344,32 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uin
     B[i] = c1[cv * N + i];
     D[i] = c2[cv * N + i];
   }
-  for (long long v0 = g; v0 < nvec; v0 += 2 * T_all) {
-    const long long v1 = v0 + T_all;
-    const bool h1 = v1 < nvec;
-    float d0[N], d1[N], f0[N], f1[N];
-    V<T>::load(dy + v0 * N, d0);
-    V<T>::load(x + v0 * N, f0);
-    uint32_t m0 = relu ? mask[v0] : 0xffu, m1 = 0xffu;
-    if (h1) {
-      V<T>::load(dy + v1 * N, d1);
-      V<T>::load(x + v1 * N, f1);
-      if (relu) m1 = mask[v1];
-    }
+  for (long long v0 = g; v0 < nvec; v0 += U * T_all) {
+    float d[U][N], f[U][N];
+    uint32_t m[U];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const float dz = (m0 >> i) & 1u ? d0[i] : 0.f;
-      d0[i] = dz;
-      f0[i] = fmaf(A[i], dz, fmaf(B[i], f0[i], D[i]));
-    }
-    V<T>::store(dx + v0 * N, f0);
-    if (dz_out) V<T>::store(dz_out + v0 * N, d0);
-    if (h1) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const float dz = (m1 >> i) & 1u ? d1[i] : 0.f;
-        d1[i] = dz;
-        f1[i] = fmaf(A[i], dz, fmaf(B[i], f1[i], D[i]));
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * T_all;
+      m[u] = 0xffu;
+      if (v < nvec) {
+        V<T>::load(dy + v * N, d[u]);
+        V<T>::load(x + v * N, f[u]);
+        if (relu) m[u] = mask[v];
       }
-      V<T>::store(dx + v1 * N, f1);
-      if (dz_out) V<T>::store(dz_out + v1 * N, d1);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * T_all;
+      if (v < nvec) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float dz = (m[u] >> i) & 1u ? d[u][i] : 0.f;
+          d[u][i] = dz;
+          f[u][i] = fmaf(A[i], dz, fmaf(B[i], f[u][i], D[i]));
+        }
+        store_streaming<T>(dx + v * N, f[u]);
+        if (dz_out) store_streaming<T>(dz_out + v * N, d[u]);
+      }
     }
   }
 }

@@ -67,8 +67,23 @@ class ResNet(nn.Module):
         self.blocks = nn.Sequential(*blocks)
         self.fc = nn.Linear(cin, num_classes)
 
+    def _stem(self, x):
+        """7x7 / stride-2 stem.  On the fused path the input goes through one space-to-depth kernel (which also does
+        the bf16 / channels-last cast) and the convolution runs as a dense 4x4 / stride-1 convolution over 16
+        channels - the same arithmetic (the 7x7 weights are re-indexed, zero taps added), 3.1x faster in cuDNN than
+        the 3-channel original (benchmarks/stem_bench.py)."""
+        if self.fused and self.training:
+            from spark_deep_learning_b200.ops import norm, pool
+            if pool.stem_s2d_supported(x) and self.stem.conv.weight.dtype == torch.bfloat16:
+                w = pool.stem_s2d_weight(self.stem.conv.weight).contiguous(memory_format=torch.channels_last)
+                y = torch.nn.functional.conv2d(pool.stem_s2d(x), w)
+                return norm.batch_norm_act(y, self.stem.bn, None, True)
+        if x.is_cuda and x.dtype != self.stem.conv.weight.dtype:
+            x = x.to(dtype=self.stem.conv.weight.dtype, memory_format=torch.channels_last)
+        return self.stem(x)
+
     def forward(self, x):
-        x = self.stem(x)
+        x = self._stem(x)
         if self.fused and x.is_cuda:
             from spark_deep_learning_b200.ops import pool
             x = pool.max_pool_3x3_s2(x)        # 1-byte argmax, gather backward (falls back when unsupported)

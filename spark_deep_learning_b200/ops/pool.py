@@ -19,6 +19,9 @@ def _lib():
         lib.sdlc_maxpool3s2_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64]
         lib.sdlc_maxpool3s2_bwd.restype = i32
         lib.sdlc_maxpool3s2_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64]
+        i64 = ctypes.c_longlong
+        lib.sdlc_stem_s2d.restype = i32
+        lib.sdlc_stem_s2d.argtypes = [vp, vp, i32, i32, i32, i64, i64, i64, i64, i32, u64]
         _sig = True
     return lib
 
@@ -66,3 +69,34 @@ def max_pool_3x3_s2(x):
     if not supported(x):
         return torch.nn.functional.max_pool2d(x, 3, stride=2, padding=1)
     return _MaxPool3s2.apply(x)
+
+
+def stem_s2d_supported(x):
+    """True when :func:`stem_s2d` can take ``x`` ([N,3,H,W] fp32 / bf16 on a GPU, even H and W)."""
+    return (x.is_cuda and x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
+            and x.dtype in (torch.float32, torch.bfloat16))
+
+
+def stem_s2d(x):
+    """Space-to-depth view of a 3-channel image batch for the ResNet stem: ``[N,3,H,W]`` (fp32 or bf16, NCHW or
+    channels-last) -> bf16 channels-last ``[N,16,H/2+3,W/2+3]`` with channel ``(rh*2+rw)*4 + c`` holding pixel
+    ``(2h'+rh-4, 2w'+rw-4)`` (zero outside the image and for c = 3).  One streaming kernel; it also replaces the
+    fp32 -> bf16 channels-last cast of the input.  No gradient (the network input needs none)."""
+    n, _, h, w = x.shape
+    out = torch.empty((n, 16, h // 2 + 3, w // 2 + 3), dtype=torch.bfloat16, device=x.device,
+                      memory_format=torch.channels_last)
+    sn, sc, sh, sw = x.stride()
+    rc = _lib().sdlc_stem_s2d(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, h, w, sn, sc, sh, sw,
+                              6 if x.dtype == torch.float32 else 5, torch.cuda.current_stream(x.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError("sdlc_stem_s2d failed (%d)" % rc)
+    launch_counter.add(1)
+    return out
+
+
+def stem_s2d_weight(w):
+    """``[O,3,7,7]`` stem weights -> the equivalent ``[O,16,4,4]`` kernel over the space-to-depth input (plain torch
+    ops on a tiny tensor, so autograd carries the weight gradient back to the original layout)."""
+    o = w.shape[0]
+    w8 = torch.nn.functional.pad(w, (1, 0, 1, 0, 0, 1))               # [O,4,8,8]; tap i+1 = 2(a+2) + r
+    return w8.view(o, 4, 4, 2, 4, 2).permute(0, 3, 5, 1, 2, 4).reshape(o, 16, 4, 4)

@@ -82,7 +82,7 @@ def test_resnet_fused_matches_unfused():
         assert d < 0.15, (k, d)
 
 
-@pytest.mark.parametrize("shape", [(4, 64, 112, 112), (2, 16, 7, 9), (3, 8, 1, 5)])
+@pytest.mark.parametrize("shape", [(4, 64, 112, 112), (2, 16, 7, 9), (3, 8, 1, 5), (2, 8, 6, 10), (2, 32, 8, 12), (1, 8, 4, 4)])
 def test_maxpool_3x3_s2_matches_torch(shape):
     from spark_deep_learning_b200.ops import pool
     torch.manual_seed(1)
@@ -100,3 +100,28 @@ def test_maxpool_3x3_s2_matches_torch(shape):
     assert torch.allclose(x1.grad.float().sum(), x2.grad.sum(), rtol=1e-2, atol=1e-1)
     same = (x1.grad.float() - x2.grad).abs() < 1e-2
     assert same.float().mean().item() > 0.999
+
+
+def test_stem_space_to_depth_matches_direct_convolution():
+    """7x7 / stride-2 stem as a 4x4 convolution over the space-to-depth input (ops/pool.py): same numbers, forward
+    and weight gradient, for fp32 NCHW and bf16 channels-last inputs."""
+    import torch.nn.functional as F
+    from spark_deep_learning_b200.ops import pool
+    torch.manual_seed(0)
+    x = torch.randn(4, 3, 64, 96, device="cuda")
+    w = (torch.randn(64, 3, 7, 7, device="cuda") * 0.05).bfloat16().requires_grad_(True)
+    wr = w.detach().float().requires_grad_(True)
+    ref = F.conv2d(x.bfloat16().float(), wr, stride=2, padding=3)
+    for xin in (x, x.bfloat16().contiguous(memory_format=torch.channels_last)):
+        assert pool.stem_s2d_supported(xin)
+        w.grad = None
+        y = F.conv2d(pool.stem_s2d(xin), pool.stem_s2d_weight(w).contiguous(memory_format=torch.channels_last))
+        assert y.shape == ref.shape
+        err = (y.float() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 2e-2, err
+        g = torch.randn_like(ref)
+        y.backward(g.bfloat16())
+        if wr.grad is None:
+            ref.backward(g.bfloat16().float(), retain_graph=True)
+        gerr = (w.grad.float() - wr.grad).abs().max().item() / wr.grad.abs().max().item()
+        assert gerr < 3e-2, gerr
