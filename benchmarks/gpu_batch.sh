@@ -30,6 +30,7 @@ for stage in "$@"; do
     profbert)  (timeout 300 python benchmarks/step_profile.py bert 2>&1 | tail -5) > gpurun_out/step_profile_bert.log; cat gpurun_out/step_profile_bert.log ;;
     profresnet) (timeout 300 python benchmarks/step_profile.py resnet 2>&1 | tail -5) > gpurun_out/step_profile_resnet.log; cat gpurun_out/step_profile_resnet.log ;;
     sdpaprobe) (timeout 120 python benchmarks/sdpa_probe.py 2>&1 | tail -20) > gpurun_out/sdpa_probe.txt; cat gpurun_out/sdpa_probe.txt ;;
+    bnvariants) for v in 0 1 2 3 4 5; do echo "variant $v"; (SPARKDL_BN_BWD_VARIANT=$v timeout 120 python benchmarks/bn_bench.py 2>&1 | grep bwd_apply); done > gpurun_out/bn_variants.txt; cat gpurun_out/bn_variants.txt ;;
     bnbench)   (timeout 300 python benchmarks/bn_bench.py 2>&1 | tail -40) > gpurun_out/bn_bench.txt; cat gpurun_out/bn_bench.txt ;;
     convbench) (timeout 400 python benchmarks/conv_bench.py 2>&1 | tail -30) > gpurun_out/conv_bench.txt; cat gpurun_out/conv_bench.txt ;;
     stembench) (timeout 300 python benchmarks/stem_bench.py 2>&1 | tail -14) > gpurun_out/stem_bench.txt; cat gpurun_out/stem_bench.txt ;;

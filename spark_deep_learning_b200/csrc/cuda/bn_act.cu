@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 namespace bn {
 
 constexpr int kThreads = 256;
@@ -326,13 +328,12 @@ template <> __device__ __forceinline__ void store_streaming<float>(float* p, con
 // Five streams (dy, x, mask in; dx, dz out): U vectors per thread are loaded before any math or store so that enough
 // bytes are in flight to cover HBM latency, and the outputs (each read exactly once, much later, by the next backward
 // kernel) are written with streaming stores so they do not evict the inputs of this pass from L2.
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int U, bool STREAM, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask,
                     const float* __restrict__ c0, const float* __restrict__ c1, const float* __restrict__ c2,
                     T* __restrict__ dx, T* __restrict__ dz_out, long long nvec, int C, int relu) {
   constexpr int N = V<T>::N;
-  constexpr int U = 4;
   const int CV = C / N;
   const long long T_all = (long long)gridDim.x * kThreads;
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -367,8 +368,13 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uin
           d[u][i] = dz;
           f[u][i] = fmaf(A[i], dz, fmaf(B[i], f[u][i], D[i]));
         }
-        store_streaming<T>(dx + v * N, f[u]);
-        if (dz_out) store_streaming<T>(dz_out + v * N, d[u]);
+        if (STREAM) {
+          store_streaming<T>(dx + v * N, f[u]);
+          if (dz_out) store_streaming<T>(dz_out + v * N, d[u]);
+        } else {
+          V<T>::store(dx + v * N, f[u]);
+          if (dz_out) V<T>::store(dz_out + v * N, d[u]);
+        }
       }
     }
   }
@@ -444,14 +450,26 @@ int sdlc_bn_bwd(const void* dy, const void* x, const void* mask, const float* we
     bn_bwd_reduce_kernel<float><<<grid, kThreads, smem, s>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
                                                             static_cast<const uint8_t*>(mask), partial, nvec, c, relu);
   bn_bwd_finalize_kernel<<<(c + kFinX - 1) / kFinX, dim3(kFinX, kFinY), 0, s>>>(partial, grid, c, 1.f / (float)m, weight, mean, rstd, dweight, dbias, c0, c1, c2);
-  if (dtype == 5)
-    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
-                                                                static_cast<const uint8_t*>(mask), c0, c1, c2,
-                                                                static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dz), nvec, c, relu);
-  else
-    bn_bwd_apply_kernel<float><<<grid, kThreads, 0, s>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
-                                                        static_cast<const uint8_t*>(mask), c0, c1, c2, static_cast<float*>(dx),
-                                                        static_cast<float*>(dz), nvec, c, relu);
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("SPARKDL_BN_BWD_VARIANT"); variant = e ? atoi(e) : 0; }
+#define BWD_APPLY(TT, UU, ST, MB)                                                                                          \
+  bn_bwd_apply_kernel<TT, UU, ST, MB><<<grid, kThreads, 0, s>>>(static_cast<const TT*>(dy), static_cast<const TT*>(x),      \
+                                                               static_cast<const uint8_t*>(mask), c0, c1, c2,              \
+                                                               static_cast<TT*>(dx), static_cast<TT*>(dz), nvec, c, relu)
+  if (dtype == 5) {
+    switch (variant) {
+      case 1: BWD_APPLY(__nv_bfloat16, 2, true, 3); break;
+      case 2: BWD_APPLY(__nv_bfloat16, 2, false, 3); break;
+      case 3: BWD_APPLY(__nv_bfloat16, 4, false, 2); break;
+      case 4: BWD_APPLY(__nv_bfloat16, 3, true, 3); break;
+      case 5: BWD_APPLY(__nv_bfloat16, 2, false, 4); break;
+      case 6: BWD_APPLY(__nv_bfloat16, 4, true, 2); break;
+      default: BWD_APPLY(__nv_bfloat16, 2, false, 4); break;   // 64 registers -> 4 CTAs / SM: 85-89 % of the measured HBM peak (bn_variants, round 2)
+    }
+  } else {
+    BWD_APPLY(float, 4, true, 2);
+  }
+#undef BWD_APPLY
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -45,19 +45,12 @@ template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<float>(const void* p
 template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<__nv_bfloat16>(const void* p) { return mc_ld_reduce_bf16(p); }
 template <> __device__ __forceinline__ uint4 mc_ld_reduce_t<__half>(const void* p) { return mc_ld_reduce_f16(p); }
 
+// one vector of parameters: gr = summed gradient, pw = fp32 parameter (master), m1 / m2 = optimizer moments (all in
+// registers, loaded by the caller so that every load of an iteration is in flight before the first use)
 template <typename T>
-__device__ __forceinline__ void optimizer_update(float* gr, float* pw, float* __restrict__ s1, float* __restrict__ s2,
-                                                 long long k0, float scale, const OptimArgs& a) {
+__device__ __forceinline__ void optimizer_update(const float* gr, float* pw, float* m1, float* m2, float scale,
+                                                 const OptimArgs& a, float inv_sqrt_bc2, float step_size) {
   using Tr = VecTraits<T>;
-  float m1[Tr::N], m2[Tr::N];
-  if (a.kind != 0 || a.momentum != 0.f) {
-#pragma unroll
-    for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(m1 + i) = *reinterpret_cast<const float4*>(s1 + k0 + i);
-  }
-  if (a.kind != 0) {
-#pragma unroll
-    for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(m2 + i) = *reinterpret_cast<const float4*>(s2 + k0 + i);
-  }
 #pragma unroll
   for (int i = 0; i < Tr::N; ++i) {
     float gi = gr[i] * scale, p = pw[i];
@@ -76,18 +69,10 @@ __device__ __forceinline__ void optimizer_update(float* gr, float* pw, float* __
       const float v = fmaf(a.beta2, m2[i], (1.f - a.beta2) * gi * gi);
       m1[i] = m;
       m2[i] = v;
-      const float denom = sqrtf(v) / sqrtf(a.bias_c2) + a.eps;
-      p = fmaf(-(a.lr / a.bias_c1), m / denom, p);
+      const float denom = fmaf(sqrtf(v), inv_sqrt_bc2, a.eps);
+      p = fmaf(-step_size, __fdividef(m, denom), p);
     }
     pw[i] = p;
-  }
-  if (a.kind != 0 || a.momentum != 0.f) {
-#pragma unroll
-    for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(s1 + k0 + i) = *reinterpret_cast<const float4*>(m1 + i);
-  }
-  if (a.kind != 0) {
-#pragma unroll
-    for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(s2 + k0 + i) = *reinterpret_cast<const float4*>(m2 + i);
   }
 }
 
@@ -104,6 +89,8 @@ fused_step_kernel(CollCtx g, PeerPtrs params, void* params_mc, float* __restrict
   const long long lo = min(nvec, (long long)g.rank * per), hi = min(nvec, lo + per);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool mc_in = g.mc != nullptr, mc_out = params_mc != nullptr;
+  const bool use_m1 = a.kind != 0 || a.momentum != 0.f, use_m2 = a.kind != 0;
+  const float inv_sqrt_bc2 = rsqrtf(a.bias_c2), step_size = a.lr / a.bias_c1;
   constexpr int U = 2;   // vectors per thread per iteration: all gradient loads are issued before any math
   for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += U * stride) {
     float gr[U][Tr::N];
@@ -119,28 +106,49 @@ fused_step_kernel(CollCtx g, PeerPtrs params, void* params_mc, float* __restrict
       for (int u = 0; u < U; ++u)
         if (valid[u]) vec_unpack<T>(v[u], gr[u]);
     } else {
-      uint4 v[U][kMaxPeers];
+      // P2P fallback (no multicast): one peer at a time, U vectors in flight per peer - the loads of all peers at
+      // once would need U x 8 x 4 registers and spill
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         valid[u] = i0 + u * stride < hi;
-        if (valid[u]) {
 #pragma unroll
-          for (int p = 0; p < kMaxPeers; ++p)
-            if (p < world) v[u][p] = ld_peer_v4(static_cast<const uint4*>(g.data.p[p]) + i0 + u * stride);
+        for (int i = 0; i < Tr::N; ++i) gr[u][i] = 0.f;
+      }
+      for (int p = 0; p < world; ++p) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (valid[u]) v[u] = ld_peer_v4(static_cast<const uint4*>(g.data.p[p]) + i0 + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!valid[u]) continue;
+          float t[Tr::N];
+          vec_unpack<T>(v[u], t);
+#pragma unroll
+          for (int i = 0; i < Tr::N; ++i) gr[u][i] += t[i];
         }
       }
+    }
+    // optimizer state of all U vectors: issued back to back (with the gradient loads above still in flight)
+    float pw[U][Tr::N], m1[U][Tr::N], m2[U][Tr::N];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!valid[u]) continue;
-        float t[Tr::N];
-        vec_unpack<T>(v[u][0], gr[u]);
+    for (int u = 0; u < U; ++u) {
+      if (!valid[u]) continue;
+      const long long idx = i0 + u * stride;
+      const long long k0 = (idx - lo) * Tr::N;
+      if (master != nullptr) {
 #pragma unroll
-        for (int p = 1; p < kMaxPeers; ++p)
-          if (p < world) {
-            vec_unpack<T>(v[u][p], t);
+        for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(pw[u] + i) = __ldcs(reinterpret_cast<const float4*>(master + k0 + i));
+      } else {
+        vec_unpack<T>(static_cast<const uint4*>(params.p[g.rank])[idx], pw[u]);
+      }
+      if (use_m1) {
 #pragma unroll
-            for (int i = 0; i < Tr::N; ++i) gr[u][i] += t[i];
-          }
+        for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(m1[u] + i) = __ldcs(reinterpret_cast<const float4*>(s1 + k0 + i));
+      }
+      if (use_m2) {
+#pragma unroll
+        for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(m2[u] + i) = __ldcs(reinterpret_cast<const float4*>(s2 + k0 + i));
       }
     }
 #pragma unroll
@@ -148,19 +156,20 @@ fused_step_kernel(CollCtx g, PeerPtrs params, void* params_mc, float* __restrict
       if (!valid[u]) continue;
       const long long idx = i0 + u * stride;
       const long long k0 = (idx - lo) * Tr::N;
-      float pw[Tr::N];
+      optimizer_update<T>(gr[u], pw[u], m1[u], m2[u], scale, a, inv_sqrt_bc2, step_size);
+      if (use_m1) {
+#pragma unroll
+        for (int i = 0; i < Tr::N; i += 4) __stcs(reinterpret_cast<float4*>(s1 + k0 + i), *reinterpret_cast<const float4*>(m1[u] + i));
+      }
+      if (use_m2) {
+#pragma unroll
+        for (int i = 0; i < Tr::N; i += 4) __stcs(reinterpret_cast<float4*>(s2 + k0 + i), *reinterpret_cast<const float4*>(m2[u] + i));
+      }
       if (master != nullptr) {
 #pragma unroll
-        for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(pw + i) = *reinterpret_cast<const float4*>(master + k0 + i);
-      } else {
-        vec_unpack<T>(static_cast<const uint4*>(params.p[g.rank])[idx], pw);
+        for (int i = 0; i < Tr::N; i += 4) __stcs(reinterpret_cast<float4*>(master + k0 + i), *reinterpret_cast<const float4*>(pw[u] + i));
       }
-      optimizer_update<T>(gr[u], pw, s1, s2, k0, scale, a);
-      if (master != nullptr) {
-#pragma unroll
-        for (int i = 0; i < Tr::N; i += 4) *reinterpret_cast<float4*>(master + k0 + i) = *reinterpret_cast<const float4*>(pw + i);
-      }
-      const uint4 out = vec_pack<T>(pw);
+      const uint4 out = vec_pack<T>(pw[u]);
       if (mc_out) {
         mc_st_v4(static_cast<uint4*>(params_mc) + idx, out);
       } else {

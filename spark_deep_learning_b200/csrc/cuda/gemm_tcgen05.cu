@@ -234,8 +234,14 @@ __device__ __forceinline__ float dgelu(float z, int kind) {
     const float t = tanh_approx(k0 * fmaf(k1 * z * z, z, z));
     return 0.5f * (1.f + t) + 0.5f * z * (1.f - t * t) * k0 * fmaf(3.f * k1 * z, z, 1.f);
   }
-  const float cdf = 0.5f * (1.f + fast_erf(z * 0.7071067811865476f));
-  return fmaf(z * __expf(-0.5f * z * z), 0.3989422804014327f, cdf);
+  // erf(z / sqrt2) = sign(z) (1 - P(t) e), t = 1 / (1 + 0.3275911 |z| / sqrt2), e = exp(-z^2 / 2): the same exponential
+  // is the Gaussian density of the second term, so one MUFU.EX2 and one MUFU.RCP serve both
+  const float a = fabsf(z) * 0.7071067811865476f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, a, 1.f));
+  const float e = __expf(-0.5f * z * z);
+  const float pe = e * t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float cdf = z >= 0.f ? 1.f - 0.5f * pe : 0.5f * pe;
+  return fmaf(z * e, 0.3989422804014327f, cdf);
 }
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }

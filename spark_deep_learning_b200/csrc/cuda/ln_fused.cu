@@ -51,9 +51,12 @@ __device__ __forceinline__ uint4 philox(uint4 c, uint2 k) {
 }
 
 // x, a, y, z: [T, H] bf16 (a may be null: plain LayerNorm(x)); gamma/beta: [H] bf16; mask: [T*H/8] bytes;
-// mean/rstd: [T] fp32; rng: device uint64 {seed, offset}; NV = H / 256 vectors per lane
+// mean/rstd: [T] fp32; rng: device uint64 {seed, offset}; NV = H / 256 vectors per lane.
+// One warp per row, ONE row per warp where the grid allows it: the only per-thread state is the row itself
+// (gamma / beta are re-read through L1 in the output phase), so 3 CTAs fit per SM and a 4096-row call is a single wave
+// (round 1 kept gamma/beta in 64 registers: 164 registers, 1 CTA / SM, 18.5 us for 32 MB of traffic).
 template <int NV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NV >= 4 ? 2 : 3)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ z,
               uint8_t* __restrict__ mask, float* __restrict__ mean, float* __restrict__ rstd,
@@ -61,12 +64,6 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * kWarps;
-  float g[NV][8], b[NV][8];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    unpack8(*reinterpret_cast<const uint4*>(gamma + (lane + 32 * v) * 8), g[v]);
-    unpack8(*reinterpret_cast<const uint4*>(beta + (lane + 32 * v) * 8), b[v]);
-  }
   const bool drop = a != nullptr && p > 0.f;
   const float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
   const uint32_t thresh = (uint32_t)(p * 65536.f);
@@ -78,14 +75,21 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
   }
   for (long long row = warp; row < T; row += nwarps) {
     float zf[NV][8];
+    uint4 xv[NV], av[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {   // all loads of the row first
+      const long long vi = row * (H / 8) + lane + 32 * v;
+      xv[v] = reinterpret_cast<const uint4*>(x)[vi];
+      if (a != nullptr) av[v] = reinterpret_cast<const uint4*>(a)[vi];
+    }
     float s = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const long long vi = row * (H / 8) + lane + 32 * v;
-      unpack8(reinterpret_cast<const uint4*>(x)[vi], zf[v]);
+      unpack8(xv[v], zf[v]);
       if (a != nullptr) {
         float af[8];
-        unpack8(reinterpret_cast<const uint4*>(a)[vi], af);
+        unpack8(av[v], af);
         uint32_t m = 0xffu;
         if (drop) {
           const uint4 r = philox(make_uint4((uint32_t)vi, (uint32_t)(vi >> 32), (uint32_t)off, call_id ^ (uint32_t)(off >> 32)), key);
@@ -120,9 +124,11 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
     for (int v = 0; v < NV; ++v) {
       const long long vi = row * (H / 8) + lane + 32 * v;
       if (z != nullptr) reinterpret_cast<uint4*>(z)[vi] = pack8(zf[v]);
-      float o[8];
+      float g[8], b[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + lane + 32 * v), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + lane + 32 * v), b);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf((zf[v][i] - mu) * rs, g[v][i], b[v][i]);
+      for (int i = 0; i < 8; ++i) o[i] = fmaf((zf[v][i] - mu) * rs, g[i], b[i]);
       reinterpret_cast<uint4*>(y)[vi] = pack8(o);
     }
   }
@@ -130,54 +136,50 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 
 __global__ void rng_advance_kernel(unsigned long long* rng) { rng[1] += 1; }
 
-// backward: dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = gamma * dy ;  dx = dz ;  da = dz * mask / (1-p)
-// partial: [gridDim.x, 2H] fp32 (dgamma, dbeta partial sums of this block's rows)
+// backward, row pass: dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = gamma * dy ;  dx = dz ;
+// da = dz * mask / (1-p).  The row stays packed (bf16) in registers between the two phases.
 template <int NV>
-__global__ void __launch_bounds__(kThreads)
-ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ gamma,
-              const uint8_t* __restrict__ mask, const float* __restrict__ mean, const float* __restrict__ rstd,
-              __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ da, float* __restrict__ partial, int T, float p) {
+__global__ void __launch_bounds__(kThreads, NV >= 3 ? 2 : 3)
+ln_bwd_row_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ gamma,
+                  const uint8_t* __restrict__ mask, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ da, int T, float p) {
   constexpr int H = NV * 256;
-  __shared__ float acc_s[2 * H];
-  for (int i = threadIdx.x; i < 2 * H; i += kThreads) acc_s[i] = 0.f;
-  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * kWarps;
-  float g[NV][8], dg[NV][8], db[NV][8];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    unpack8(*reinterpret_cast<const uint4*>(gamma + (lane + 32 * v) * 8), g[v]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { dg[v][i] = 0.f; db[v][i] = 0.f; }
-  }
   const float keep_scale = (da != nullptr && p > 0.f) ? 1.f / (1.f - p) : 1.f;
   for (long long row = warp; row < T; row += nwarps) {
     const float mu = mean[row], rs = rstd[row];
-    float gy[NV][8], xh[NV][8];
-    float s1 = 0.f, s2 = 0.f;
+    uint4 dv[NV], zv[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const long long vi = row * (H / 8) + lane + 32 * v;
-      float d[8], zf[8];
-      unpack8(reinterpret_cast<const uint4*>(dy)[vi], d);
-      unpack8(reinterpret_cast<const uint4*>(z)[vi], zf);
+      dv[v] = reinterpret_cast<const uint4*>(dy)[vi];
+      zv[v] = reinterpret_cast<const uint4*>(z)[vi];
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float d[8], zf[8], g[8];
+      unpack8(dv[v], d);
+      unpack8(zv[v], zf);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + lane + 32 * v), g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        xh[v][i] = (zf[i] - mu) * rs;
-        db[v][i] += d[i];
-        dg[v][i] = fmaf(d[i], xh[v][i], dg[v][i]);
-        gy[v][i] = d[i] * g[v][i];
-        s1 += gy[v][i];
-        s2 = fmaf(gy[v][i], xh[v][i], s2);
+        const float gy = d[i] * g[i];
+        s1 += gy;
+        s2 = fmaf(gy, (zf[i] - mu) * rs, s2);
       }
     }
     const float m1 = warp_sum(s1) * (1.f / H), m2 = warp_sum(s2) * (1.f / H);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const long long vi = row * (H / 8) + lane + 32 * v;
-      float o[8];
+      float d[8], zf[8], g[8], o[8];
+      unpack8(dv[v], d);
+      unpack8(zv[v], zf);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + lane + 32 * v), g);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = rs * (gy[v][i] - m1 - xh[v][i] * m2);
+      for (int i = 0; i < 8; ++i) o[i] = rs * (d[i] * g[i] - m1 - (zf[i] - mu) * rs * m2);
       reinterpret_cast<uint4*>(dx)[vi] = pack8(o);
       if (da != nullptr) {
         const uint32_t m = (p > 0.f) ? mask[vi] : 0xffu;
@@ -187,17 +189,61 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       }
     }
   }
-  // combine the 8 warps of the block (shared-memory atomics, 2H addresses), then one partial row per block
+}
+
+// backward, column pass: partial[b][0:H] = sum_rows dy * xhat, partial[b][H:2H] = sum_rows dy over the rows of block b.
+// One thread per 8-column vector, rows of the slice streamed 4 at a time (the second read of dy / z mostly hits L2).
+__global__ void __launch_bounds__(128)
+ln_bwd_col_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, float* __restrict__ partial, int T, int H) {
+  const int cv = threadIdx.x;
+  if (cv >= H / 8) return;
+  const int R = gridDim.x;
+  const int rows_per = (T + R - 1) / R;
+  const int r0 = blockIdx.x * rows_per, r1 = min(T, r0 + rows_per);
+  float dg[8], db[8];
 #pragma unroll
-  for (int v = 0; v < NV; ++v)
+  for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    uint4 dv[4], zv[4];
+    float mu[4], rs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dv[u] = reinterpret_cast<const uint4*>(dy)[(long long)(r + u) * (H / 8) + cv];
+      zv[u] = reinterpret_cast<const uint4*>(z)[(long long)(r + u) * (H / 8) + cv];
+      mu[u] = mean[r + u];
+      rs[u] = rstd[r + u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float d[8], zf[8];
+      unpack8(dv[u], d);
+      unpack8(zv[u], zf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        db[i] += d[i];
+        dg[i] = fmaf(d[i], (zf[i] - mu[u]) * rs[u], dg[i]);
+      }
+    }
+  }
+  for (; r < r1; ++r) {
+    float d[8], zf[8];
+    unpack8(reinterpret_cast<const uint4*>(dy)[(long long)r * (H / 8) + cv], d);
+    unpack8(reinterpret_cast<const uint4*>(z)[(long long)r * (H / 8) + cv], zf);
+    const float mu = mean[r], rs = rstd[r];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = (lane + 32 * v) * 8 + i;
-      atomicAdd(&acc_s[c], dg[v][i]);
-      atomicAdd(&acc_s[H + c], db[v][i]);
+      db[i] += d[i];
+      dg[i] = fmaf(d[i], (zf[i] - mu) * rs, dg[i]);
     }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * H; i += kThreads) partial[(long long)blockIdx.x * 2 * H + i] = acc_s[i];
+  }
+  float* out = partial + (long long)blockIdx.x * 2 * H + cv * 8;
+#pragma unroll
+  for (int i = 0; i < 8; i += 4) {
+    *reinterpret_cast<float4*>(out + i) = make_float4(dg[i], dg[i + 1], dg[i + 2], dg[i + 3]);
+    *reinterpret_cast<float4*>(out + H + i) = make_float4(db[i], db[i + 1], db[i + 2], db[i + 3]);
+  }
 }
 
 // dgamma/dbeta = sum over blocks of the partial rows: 32 columns x 32 row-groups per block (the loop over partial
@@ -220,8 +266,14 @@ ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, fl
   }
 }
 
-static int grid_rows(int T) {
+static int grid_rows(int T) {   // row kernels: one row per warp where possible, at most 3 CTAs per SM
   long long blocks = (T + kWarps - 1) / kWarps;
+  if (blocks > 148 * 3) blocks = 148 * 3;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+static int grid_cols(int T) {   // column kernel: number of row slices (= partial rows)
+  long long blocks = (T + 15) / 16;
   if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -234,7 +286,7 @@ using namespace lnf;
 extern "C" {
 
 int sdlc_ln_supported(int H) { return H == 256 || H == 512 || H == 768 || H == 1024; }
-int sdlc_ln_grid(int T) { return grid_rows(T); }
+int sdlc_ln_grid(int T) { return grid_cols(T); }   // partial rows of the backward column pass
 
 #define LN_DISPATCH(NVV, CALL)                                                                                      \
   switch (NVV) {                                                                                                    \
@@ -264,11 +316,12 @@ int sdlc_ln_bwd(const void* dy, const void* z, const void* gamma, const void* ma
                 unsigned long long stream) {
   if (!sdlc_ln_supported(H)) return -2;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = grid_rows(T);
+  const int grid = grid_rows(T), cgrid = grid_cols(T);
   typedef const __nv_bfloat16* B;
-  LN_DISPATCH(H / 256, (ln_bwd_kernel<NV><<<grid, kThreads, 0, s>>>((B)dy, (B)z, (B)gamma, (const uint8_t*)mask, mean, rstd,
-                                                                    (__nv_bfloat16*)dx, (__nv_bfloat16*)da, partial, T, p)));
-  ln_bwd_finalize_kernel<<<(2 * H + 31) / 32, dim3(32, 32), 0, s>>>(partial, grid, H, dgamma, dbeta);
+  LN_DISPATCH(H / 256, (ln_bwd_row_kernel<NV><<<grid, kThreads, 0, s>>>((B)dy, (B)z, (B)gamma, (const uint8_t*)mask, mean, rstd,
+                                                                        (__nv_bfloat16*)dx, (__nv_bfloat16*)da, T, p)));
+  ln_bwd_col_kernel<<<cgrid, 128, 0, s>>>((B)dy, (B)z, mean, rstd, partial, T, H);
+  ln_bwd_finalize_kernel<<<(2 * H + 31) / 32, dim3(32, 32), 0, s>>>(partial, cgrid, H, dgamma, dbeta);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
