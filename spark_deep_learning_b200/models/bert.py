@@ -103,7 +103,12 @@ class BertForPreTraining(nn.Module):
         nsp_logits = self.nsp(pooled)
         if labels is None:
             return logits[..., :self.vocab], nsp_logits
-        loss = F.cross_entropy(logits.view(-1, self.vocab_padded).float(), labels.view(-1))
+        flat, lab = logits.view(-1, self.vocab_padded), labels.reshape(-1)
+        if self.fused and flat.is_cuda and flat.dtype == torch.bfloat16:
+            from spark_deep_learning_b200.ops import xent
+            loss = xent.cross_entropy(flat, lab)          # one pass each way over the [tokens, vocab] matrix, no fp32 copy
+        else:
+            loss = F.cross_entropy(flat.float(), lab)
         if next_sentence_label is None:
             next_sentence_label = torch.zeros(b, dtype=torch.long, device=input_ids.device)
         return loss + F.cross_entropy(nsp_logits.float(), next_sentence_label)

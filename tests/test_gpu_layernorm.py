@@ -59,3 +59,19 @@ def test_dropout_masks_change_between_calls():
     m1, m2 = y1.grad_fn.saved_tensors[1], y2.grad_fn.saved_tensors[1]
     assert not torch.equal(m1, m2)
     assert abs(float(y1.float().mean()) ) < 1.0
+
+
+def test_fused_cross_entropy_matches_torch():
+    from spark_deep_learning_b200.ops import xent
+    torch.manual_seed(0)
+    for (t, v) in [(64, 1000), (300, 30528), (7, 8)]:
+        logits = (torch.randn(t, v, device="cuda") * 3).bfloat16().requires_grad_(True)
+        labels = torch.randint(0, v, (t,), device="cuda")
+        ref_in = logits.detach().float().requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(ref_in, labels)
+        ref.backward()
+        loss = xent.cross_entropy(logits, labels)
+        (loss * 2.0).backward()
+        assert abs(float(loss) - float(ref)) < 2e-3 * abs(float(ref)), (float(loss), float(ref))
+        err = (logits.grad.float() - 2.0 * ref_in.grad).abs().max().item() / (2.0 * ref_in.grad.abs().max().item())
+        assert err < 1e-2, err
