@@ -35,6 +35,9 @@ for stage in "$@"; do
     convbench) (timeout 400 python benchmarks/conv_bench.py 2>&1 | tail -30) > gpurun_out/conv_bench.txt; cat gpurun_out/conv_bench.txt ;;
     stembench) (timeout 300 python benchmarks/stem_bench.py 2>&1 | tail -14) > gpurun_out/stem_bench.txt; cat gpurun_out/stem_bench.txt ;;
     lntest)    (timeout 300 python -m pytest tests/test_gpu_layernorm.py -q -m gpu 2>&1 | tail -5) > gpurun_out/pytest_ln.txt; cat gpurun_out/pytest_ln.txt ;;
+    capprobe)  (timeout 200 python benchmarks/capture_probe.py 2>&1 | grep -E "CAPTURE|eager|Error|error" | tail -20) > gpurun_out/capture_probe.txt; cat gpurun_out/capture_probe.txt
+               (HID=1024 timeout 200 python benchmarks/capture_probe.py 2>&1 | grep -E "CAPTURE|eager|Error|error" | tail -20) > gpurun_out/capture_probe_1024.txt; cat gpurun_out/capture_probe_1024.txt ;;
+    capprobe2) (timeout 200 python benchmarks/capture_probe2.py 2>&1 | grep -E "CAPTURE|Error|error" | tail -20) > gpurun_out/capture_probe2.txt; cat gpurun_out/capture_probe2.txt ;;
     bertprobe) (timeout 200 python benchmarks/bert_sink_probe.py 2>&1 | tail -40) > gpurun_out/bert_sink_probe.txt; tail -25 gpurun_out/bert_sink_probe.txt ;;
     gemmstaging) for d in 1 2; do (SPARKDL_GEMM_STAGING=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | sed "s/^dbg=0/staging=$d/" | tail -10); done > gpurun_out/gemm_staging.txt; cat gpurun_out/gemm_staging.txt ;;
     gemmlab)   for d in 0 1 2 3 4; do (SPARKDL_GEMM_DBG=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | grep -v cublas | tail -8); done > gpurun_out/gemm_lab.txt

@@ -703,7 +703,7 @@ def train(params, X, y, weight=None, eval_set=None, base_margin=None, eval_base_
         booster = Booster(objective, num_class, float(p["base_score"]), missing, F)
     cuts = compute_cuts(X, missing, int(p["max_bin"]), dist, seed=int(p["random_state"] or 0))
     bins = bin_features(X, cuts, missing)
-    builder = _HistBuilder(bins, dist)
+    builder = _HistBuilder(bins, dist, use_fused=os.environ.get("SPARKDL_GBDT_FUSED", "1") != "0")
 
     margin = booster.predict_margin(X, base_margin)
     ev = None
