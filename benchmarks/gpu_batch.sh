@@ -38,6 +38,8 @@ for stage in "$@"; do
     capprobe)  (timeout 200 python benchmarks/capture_probe.py 2>&1 | grep -E "CAPTURE|eager|Error|error" | tail -20) > gpurun_out/capture_probe.txt; cat gpurun_out/capture_probe.txt
                (HID=1024 timeout 200 python benchmarks/capture_probe.py 2>&1 | grep -E "CAPTURE|eager|Error|error" | tail -20) > gpurun_out/capture_probe_1024.txt; cat gpurun_out/capture_probe_1024.txt ;;
     capprobe2) (timeout 200 python benchmarks/capture_probe2.py 2>&1 | grep -E "CAPTURE|Error|error" | tail -20) > gpurun_out/capture_probe2.txt; cat gpurun_out/capture_probe2.txt ;;
+    sweep)     NPX=${SWEEP_NP:-2}; (timeout 900 python benchmarks/allreduce_sweep.py --np $NPX --max-mb ${SWEEP_MB:-256} --out gpurun_out/allreduce_sweep_np$NPX.json 2>&1 | tail -3) > gpurun_out/sweep_np$NPX.log; tail -2 gpurun_out/sweep_np$NPX.log ;;
+    collsweep) NPX=${SWEEP_NP:-2}; (timeout 900 python benchmarks/collective_sweep.py --np $NPX --max-mb ${SWEEP_MB:-256} --out gpurun_out/collective_sweep_np$NPX.json 2>&1 | tail -3) > gpurun_out/collsweep_np$NPX.log; tail -2 gpurun_out/collsweep_np$NPX.log ;;
     bertprobe) (timeout 200 python benchmarks/bert_sink_probe.py 2>&1 | tail -40) > gpurun_out/bert_sink_probe.txt; tail -25 gpurun_out/bert_sink_probe.txt ;;
     gemmstaging) for d in 1 2; do (SPARKDL_GEMM_STAGING=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | sed "s/^dbg=0/staging=$d/" | tail -10); done > gpurun_out/gemm_staging.txt; cat gpurun_out/gemm_staging.txt ;;
     gemmlab)   for d in 0 1 2 3 4; do (SPARKDL_GEMM_DBG=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | grep -v cublas | tail -8); done > gpurun_out/gemm_lab.txt

@@ -506,10 +506,17 @@ __global__ void __launch_bounds__(256) scale_kernel(T* p, long long n, float s) 
 }
 
 // ---- host-side dispatch ----------------------------------------------------------------------------------
+// CTAs of a bandwidth kernel.  `max_blocks` (SPARKDL_COMM_CTAS, default 32) is tuned for 8 ranks, where every thread
+// keeps loads to 7 peers in flight; with fewer peers a CTA has proportionally fewer bytes in flight over NVLink
+// (round 1: 357-400 GB/s at np=2 with 32 CTAs vs 508 GB/s for NCCL), so the cap scales with 8 / world.  The result
+// depends on rank-independent values only (the in-kernel barrier pairs CTA b of every rank).
 static int pick_blocks(const Comm* c, long long work_items, int per_block) {
   long long b = ceil_div_ll(work_items, per_block);
   if (b < 1) b = 1;
-  if (b > c->max_blocks) b = c->max_blocks;
+  long long cap = c->max_blocks;
+  if (c->world > 1 && c->world < 8) cap = cap * (8 / c->world);
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  if (b > cap) b = cap;
   return (int)b;
 }
 
@@ -532,7 +539,9 @@ static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int 
   if (algo == 0) {
     if (c->world == 1) algo = 1;
     else if (bytes <= (long long)c->oneshot_max_bytes && nvec <= (long long)c->max_blocks * kThreads * kOneShotR) algo = 1;
-    else if (ctx.mc != nullptr && mc_type && op == kSum) algo = 3;
+    // in-switch reduction halves the bytes a rank receives only when there are >= 3 peers to fold: at 2 ranks the
+    // P2P two-shot moves the same bytes and measures 1.6x faster (417 vs 696 us at 256 MB, sweep of round 2)
+    else if (ctx.mc != nullptr && mc_type && op == kSum && c->world > 2) algo = 3;
     else algo = 2;
   }
   if (algo == 1) {
