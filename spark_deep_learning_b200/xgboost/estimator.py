@@ -145,7 +145,89 @@ class _XgboostEstimator(Estimator, _XgboostParams, MLReadable, MLWritable):
     def _model_class(self):
         raise NotImplementedError()
 
+    def _fit_on_spark(self, dataset, num_workers):
+        """Spark-native training: "Each XGBoost worker corresponds to one spark task" (ref ``xgboost.py:58-64``) - the
+        rows never visit the driver.  The (re)partitioned DataFrame runs ONE barrier stage with ``num_workers`` tasks;
+        every task turns its partition into a shard, joins the collective gang (``parallel/spark_gang.py``) and trains
+        with histogram allreduce; task 0 returns the model."""
+        from spark_deep_learning_b200.parallel import spark_gang
+        gv = self.getOrDefault
+        fcol, lcol, wcol, vcol = gv("featuresCol"), gv("labelCol"), gv("weightCol"), gv("validationIndicatorCol")
+        have = set(dataset.columns)
+        wcol = wcol if wcol and wcol in have else None
+        vcol = vcol if vcol and vcol in have else None
+        if gv("baseMarginCol") and gv("baseMarginCol") in have:
+            raise ValueError("baseMarginCol is not available for distributed training")
+        df = dataset.select(*[c for c in (fcol, lcol, wcol, vcol) if c])
+        if bool(gv("force_repartition")) or df.rdd.getNumPartitions() != num_workers:
+            df = df.repartition(num_workers)
+        params = self._gbdt_params()
+        is_clf, default_obj = self._is_classifier, self._objective_default
+        extra = dict(missing=float(gv("missing")), xgb_model=gv("xgb_model"), callbacks=gv("callbacks"))
+        use_gpu = bool(gv("use_gpu"))
+
+        def task(rows):
+            import numpy as _np
+            from pyspark import BarrierTaskContext
+            from spark_deep_learning_b200.parallel import spark_gang as sg
+            from spark_deep_learning_b200.xgboost import gbdt as g
+            from spark_deep_learning_b200.xgboost.linalg import features_to_matrix as f2m
+            ctx = BarrierTaskContext.get()
+            if not use_gpu:
+                os.environ["SPARKDL_FORCE_CPU"] = "1"
+            rank, server, _lines = sg.enter_gang(ctx, num_workers, tag="xgb")
+            out = None
+            try:
+                rows = list(rows)
+                if not rows:
+                    raise ValueError("xgboost worker %d received an empty partition; use force_repartition=True" % rank)
+                X = f2m([r[fcol] for r in rows])
+                y = _np.asarray([r[lcol] for r in rows], dtype=_np.float32)
+                w = _np.asarray([r[wcol] for r in rows], dtype=_np.float32) if wcol else None
+                val = _np.asarray([bool(r[vcol]) for r in rows]) if vcol else _np.zeros(len(y), dtype=bool)
+                import torch
+                import sparkdl.hvd as hvd
+                hvd.init()
+                p = dict(params)
+                if is_clf:
+                    ymax = float(_np.nanmax(y)) if len(y) else 0.0
+                    n_class = int(hvd.allreduce(torch.tensor([ymax]), op=hvd.Max, name="xgb.nclass")[0].item()) + 1
+                    if p["objective"] is None:
+                        p["objective"] = "binary:logistic" if n_class <= 2 else "multi:softprob"
+                    if p["objective"].startswith("multi:"):
+                        p["num_class"] = n_class
+                elif p["objective"] is None:
+                    p["objective"] = default_obj
+                any_val = bool(hvd.allreduce(torch.tensor([float(val.any())]), op=hvd.Max, name="xgb.anyval")[0].item())
+                tr = ~val
+                booster, evals = g.train(params=p, X=X[tr], y=y[tr], weight=None if w is None else w[tr],
+                                         eval_set=(X[val], y[val], None if w is None else w[val]) if any_val else None,
+                                         base_margin=None, eval_base_margin=None, **extra)
+                if rank == 0:
+                    out = (booster.to_json(), evals)
+            finally:
+                sg.leave_gang(ctx, server)
+            if rank == 0:
+                yield out
+
+        slots = spark_gang.total_slots(dataset.sparkSession.sparkContext)
+        if num_workers > slots:
+            raise RuntimeError("num_workers=%d needs %d Spark task slots, the cluster has %d" % (num_workers, num_workers, slots))
+        js, evals = df.rdd.barrier().mapPartitions(task).collect()[0]
+        return gbdt.Booster.from_json(js), evals
+
+    def _finish_model(self, booster, evals):
+        model = self._model_class()(xgb_sklearn_model=booster)
+        model._evals_result = evals
+        for p in self.params:
+            if model.hasParam(p.name) and self.isDefined(p):
+                model._set(**{p.name: self.getOrDefault(p)}) if self.isSet(p) else None
+        return model
+
     def _fit(self, dataset):
+        if (hasattr(dataset, "rdd") and hasattr(dataset, "sparkSession") and int(self.getOrDefault("num_workers") or 1) > 1
+                and not self.getOrDefault("use_external_storage")):
+            return self._finish_model(*self._fit_on_spark(dataset, int(self.getOrDefault("num_workers"))))
         fr = _Frame(dataset)
         gv = self.getOrDefault
         X = features_to_matrix(fr.col(gv("featuresCol")))
@@ -181,12 +263,7 @@ class _XgboostEstimator(Estimator, _XgboostParams, MLReadable, MLWritable):
                                               int(params.get("random_state") or 0))
         else:
             booster, evals = gbdt.train(**train_args)
-        model = self._model_class()(xgb_sklearn_model=booster)
-        model._evals_result = evals
-        for p in self.params:
-            if model.hasParam(p.name) and self.isDefined(p):
-                model._set(**{p.name: self.getOrDefault(p)}) if self.isSet(p) else None
-        return model
+        return self._finish_model(booster, evals)
 
     # -- persistence -----------------------------------------------------------------------------------
     def _save_impl(self, path):

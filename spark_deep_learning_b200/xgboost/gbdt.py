@@ -262,14 +262,121 @@ class Booster(object):
         b.attributes = d.get("attributes", {})
         return b
 
+    # xgboost's own JSON model schema (what ``xgboost.Booster.save_model("m.json")`` writes and ``load_model`` reads):
+    # ``get_booster()`` of the reference returns an ``xgboost.core.Booster`` (ref ``xgboost.py:130-133``); xgboost is not
+    # installable here, so interoperability goes through the file format - a model saved with ``save_model("x.json")``
+    # opens in stock xgboost, and a gbtree model written by stock xgboost loads here.
+    _OBJ_PARAM = {"reg:": ("reg_loss_param", {"scale_pos_weight": "1"}), "binary:": ("reg_loss_param", {"scale_pos_weight": "1"}),
+                  "count:poisson": ("poisson_regression_param", {"max_delta_step": "0.7"}),
+                  "reg:tweedie": ("tweedie_regression_param", {"tweedie_variance_power": "1.5"}),
+                  "reg:pseudohubererror": ("pseudo_huber_param", {"huber_slope": "1"})}
+
+    def to_xgboost_json(self):
+        trees = []
+        for tid, t in enumerate(self.trees):
+            n = len(t.left)
+            parents = [2147483647] * n
+            for i in range(n):
+                if t.left[i] >= 0:
+                    parents[t.left[i]] = i
+                    parents[t.right[i]] = i
+            leaf = [t.left[i] < 0 for i in range(n)]
+            trees.append({
+                "base_weights": [float(v) for v in t.value], "categories": [], "categories_nodes": [],
+                "categories_segments": [], "categories_sizes": [],
+                "default_left": [int(bool(d)) for d in t.default_left], "id": tid,
+                "left_children": [int(v) for v in t.left], "loss_changes": [float(g) for g in t.gain], "parents": parents,
+                "right_children": [int(v) for v in t.right],
+                # xgboost keeps the leaf value in split_conditions of a leaf
+                "split_conditions": [float(t.value[i]) if leaf[i] else float(t.threshold[i]) for i in range(n)],
+                "split_indices": [0 if leaf[i] else int(t.feature[i]) for i in range(n)], "split_type": [0] * n,
+                "sum_hessian": [float(c) for c in t.cover],
+                "tree_param": {"num_deleted": "0", "num_feature": str(self.n_features), "num_nodes": str(n),
+                               "size_leaf_vector": "1"}})
+        npt = max(1, int(self.attributes.get("num_parallel_tree", 1)))
+        per_round = max(1, self.n_groups) * npt
+        rounds = len(self.trees) // per_round if per_round else 0
+        multi = self.objective.startswith("multi:")
+        if multi:
+            obj = {"name": self.objective, "softmax_multiclass_param": {"num_class": str(self.num_class)}}
+        else:
+            key = next((k for k in sorted(self._OBJ_PARAM, key=len, reverse=True) if self.objective.startswith(k)), "reg:")
+            pname, pval = self._OBJ_PARAM[key]
+            obj = {"name": self.objective, pname: dict(pval)}
+        attrs = {k: (v if isinstance(v, str) else json.dumps(v)) for k, v in self.attributes.items()}
+        if self.best_iteration is not None:
+            attrs["best_iteration"] = str(self.best_iteration)
+        if self.best_score is not None:
+            attrs["best_score"] = repr(float(self.best_score))
+        if not (isinstance(self.missing, float) and math.isnan(self.missing)):
+            attrs["sparkdl_missing"] = repr(float(self.missing))
+        return json.dumps({"learner": {
+            "attributes": attrs, "feature_names": [], "feature_types": [],
+            "gradient_booster": {"model": {
+                "gbtree_model_param": {"num_parallel_tree": str(npt), "num_trees": str(len(self.trees))},
+                "iteration_indptr": [i * per_round for i in range(rounds + 1)],
+                "tree_info": [int(g) for g in self.tree_group], "trees": trees}, "name": "gbtree"},
+            "learner_model_param": {"base_score": "%.9E" % float(self.base_score), "boost_from_average": "1",
+                                    "num_class": str(self.num_class if multi else 0),
+                                    "num_feature": str(self.n_features), "num_target": "1"},
+            "objective": obj}, "version": [2, 0, 3]})
+
+    @staticmethod
+    def from_xgboost_json(text):
+        d = json.loads(text) if isinstance(text, str) else text
+        L = d["learner"]
+        gb = L["gradient_booster"]
+        if gb.get("name", "gbtree") not in ("gbtree", "dart"):
+            raise ValueError("only gbtree models can be loaded, got %r" % gb.get("name"))
+        model = gb["model"] if "model" in gb else gb["gbtree"]["model"]
+        lmp = L["learner_model_param"]
+        objective = L["objective"]["name"]
+        num_class = max(1, int(lmp.get("num_class", "0")))
+        attrs = dict(L.get("attributes", {}))
+        missing = float(attrs.pop("sparkdl_missing")) if "sparkdl_missing" in attrs else float("nan")
+        b = Booster(objective, num_class, float(lmp.get("base_score", "0.5")), missing, int(lmp.get("num_feature", "0")))
+        if "best_iteration" in attrs:
+            b.best_iteration = int(attrs.pop("best_iteration"))
+        if "best_score" in attrs:
+            b.best_score = float(attrs.pop("best_score"))
+        for k, v in attrs.items():
+            try:
+                b.attributes[k] = json.loads(v)
+            except (ValueError, TypeError):
+                b.attributes[k] = v
+        npt = int(model.get("gbtree_model_param", {}).get("num_parallel_tree", "1"))
+        if npt > 1:
+            b.attributes["num_parallel_tree"] = npt
+        for t in model["trees"]:
+            if any(int(x) != 0 for x in t.get("split_type", [])):
+                raise ValueError("categorical splits are not supported")
+            tr = Tree()
+            n = len(t["left_children"])
+            for i in range(n):
+                tr.add_node()
+                leaf = t["left_children"][i] < 0
+                tr.left[i], tr.right[i] = int(t["left_children"][i]), int(t["right_children"][i])
+                tr.default_left[i] = int(t["default_left"][i])
+                tr.feature[i] = -1 if leaf else int(t["split_indices"][i])
+                tr.threshold[i] = 0.0 if leaf else float(t["split_conditions"][i])
+                tr.value[i] = float(t["split_conditions"][i]) if leaf else float(t["base_weights"][i])
+                tr.cover[i] = float(t["sum_hessian"][i])
+                tr.gain[i] = float(t["loss_changes"][i])
+            b.trees.append(tr)
+        b.tree_group = [int(g) for g in model["tree_info"]]
+        return b
+
     def save_model(self, path):
+        """``*.json`` -> xgboost's JSON model schema (opens in stock xgboost); anything else -> the native format."""
         with open(path, "w") as f:
-            f.write(self.to_json())
+            f.write(self.to_xgboost_json() if str(path).endswith(".json") else self.to_json())
 
     @staticmethod
     def load_model(path):
         with open(path) as f:
-            return Booster.from_json(f.read())
+            text = f.read()
+        d = json.loads(text)
+        return Booster.from_xgboost_json(d) if "learner" in d else Booster.from_json(text)
 
     def copy(self):
         return Booster.from_json(self.to_json())

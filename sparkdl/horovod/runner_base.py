@@ -80,6 +80,13 @@ class HorovodRunner(object):
                                    % (np_, world))
             return main(**kwargs)
 
+        if np_ > 0:
+            # cluster mode: with a live SparkSession the gang is one Spark barrier stage (runner_base.py:54-61)
+            from spark_deep_learning_b200.parallel import spark_gang
+            spark = spark_gang.active_session()
+            if spark is not None:
+                logger.info("HorovodRunner: launching a Spark barrier job with %d tasks.", np_)
+                return spark_gang.launch_on_spark(spark, main, kwargs, np_)
         num_proc = launcher.resolve_num_proc(np_)
         if num_proc == 1 and get_config(refresh=True).inprocess_single:
             # opt-in: behave like the open-source stub (same process, closures keep working)

@@ -558,3 +558,37 @@ def test_real_values_never_land_in_the_missing_bin():
     bins = gbdt.bin_features(X, cuts, float("nan"))
     assert int((bins[:, 1] == gbdt.MISSING_BIN).sum()) == int(torch.isnan(X[:, 1]).sum())
     assert int((bins[:, 0] == gbdt.MISSING_BIN).sum()) == 0
+
+
+def test_booster_round_trips_through_the_xgboost_json_schema(tmp_path):
+    """ref xgboost.py:130-133: get_booster() is an xgboost Booster; interoperability is the JSON model schema."""
+    import json
+    import torch
+    from spark_deep_learning_b200.xgboost import gbdt
+    X, y = _toy(2000)
+    df = pd.DataFrame({"features": list(X), "label": (y > y.mean()).astype(np.float32)})
+    for est, kw in ((XgboostRegressor, {}), (XgboostClassifier, {})):
+        model = est(n_estimators=6, max_depth=4, missing=0.0 if est is XgboostClassifier else float("nan"), **kw).fit(df)
+        b = model.get_booster()
+        path = str(tmp_path / ("m_%s.json" % est.__name__))
+        b.save_model(path)
+        doc = json.load(open(path))
+        gbm = doc["learner"]["gradient_booster"]["model"]
+        assert doc["version"][0] >= 1 and doc["learner"]["gradient_booster"]["name"] == "gbtree"
+        assert int(gbm["gbtree_model_param"]["num_trees"]) == len(b.trees) == len(gbm["trees"]) == len(gbm["tree_info"])
+        t0 = gbm["trees"][0]
+        for key in ("left_children", "right_children", "parents", "split_indices", "split_conditions", "default_left",
+                    "base_weights", "loss_changes", "sum_hessian", "split_type", "tree_param"):
+            assert key in t0
+        assert t0["parents"][0] == 2147483647 and int(t0["tree_param"]["num_nodes"]) == len(t0["left_children"])
+        leaf = t0["left_children"].index(-1)
+        assert t0["right_children"][leaf] == -1 and t0["split_conditions"][leaf] == t0["base_weights"][leaf]
+        assert doc["learner"]["objective"]["name"] == b.objective
+        b2 = gbdt.Booster.load_model(path)
+        Xt = torch.from_numpy(X)
+        assert torch.allclose(b.predict(Xt), b2.predict(Xt), atol=1e-6)
+        assert b2.objective == b.objective and b2.n_features == b.n_features
+        # the native format still loads
+        p2 = str(tmp_path / "native.bin")
+        b.save_model(p2)
+        assert torch.allclose(gbdt.Booster.load_model(p2).predict(Xt), b.predict(Xt))
