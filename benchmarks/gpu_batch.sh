@@ -26,7 +26,9 @@ for stage in "$@"; do
     probes)    (timeout 300 python benchmarks/resnet_probe.py 2>&1 | tail -30) > gpurun_out/resnet_probe.txt
                (timeout 300 python benchmarks/bert_probe.py 2>&1 | tail -30) > gpurun_out/bert_probe.txt
                tail -12 gpurun_out/resnet_probe.txt gpurun_out/bert_probe.txt ;;
-    xgb)       (timeout 400 python benchmarks/xgboost_bench.py --np 1 2>&1 | tail -8) > gpurun_out/xgb_np1.txt; cat gpurun_out/xgb_np1.txt ;;
+    xgb)       NPX=${XGB_NP:-1}; (timeout 300 python -m pytest tests/test_gpu_xgboost.py -q -m gpu 2>&1 | tail -5) > gpurun_out/pytest_xgb.txt; cat gpurun_out/pytest_xgb.txt
+               (timeout 400 python benchmarks/xgboost_bench.py --np $NPX --out gpurun_out/xgboost_bench_np$NPX.json 2>&1 | tail -4) > gpurun_out/xgb_np$NPX.txt; cat gpurun_out/xgb_np$NPX.txt
+               (SPARKDL_GBDT_SMEM_HIST=0 timeout 400 python benchmarks/xgboost_bench.py --np $NPX --out gpurun_out/xgboost_bench_np${NPX}_globalatomics.json 2>&1 | tail -2) > gpurun_out/xgb_np${NPX}_ga.txt; cat gpurun_out/xgb_np${NPX}_ga.txt ;;
     profbert)  (timeout 300 python benchmarks/step_profile.py bert 2>&1 | tail -5) > gpurun_out/step_profile_bert.log; cat gpurun_out/step_profile_bert.log ;;
     profresnet) (timeout 300 python benchmarks/step_profile.py resnet 2>&1 | tail -5) > gpurun_out/step_profile_resnet.log; cat gpurun_out/step_profile_resnet.log ;;
     sdpaprobe) (timeout 120 python benchmarks/sdpa_probe.py 2>&1 | tail -20) > gpurun_out/sdpa_probe.txt; cat gpurun_out/sdpa_probe.txt ;;

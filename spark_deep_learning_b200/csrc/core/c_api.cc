@@ -117,6 +117,11 @@ void sdl_release(void* e, int64_t h) { static_cast<Engine*>(e)->release(h); }
 
 uint64_t sdl_stat_responses(void* e) { return static_cast<Engine*>(e)->responses_executed(); }
 uint64_t sdl_stat_tensors(void* e) { return static_cast<Engine*>(e)->tensors_fused(); }
+uint64_t sdl_stat_cache_hits(void* e) { return static_cast<Engine*>(e)->cache_hits(); }
+uint64_t sdl_stat_cache_misses(void* e) { return static_cast<Engine*>(e)->cache_misses(); }
+uint64_t sdl_stat_cache_size(void* e) { return static_cast<Engine*>(e)->cache_size(); }
+double sdl_stat_negotiation_us(void* e) { return static_cast<Engine*>(e)->negotiation_us(); }
+void sdl_set_cache_enabled(void* e, int on) { static_cast<Engine*>(e)->set_cache_enabled(on != 0); }
 
 // stand-alone helpers (unit tests of the host reduction kernels)
 void sdl_reduce_into(void* dst, const void* src, int64_t n, uint32_t dtype, uint32_t op) {

@@ -17,6 +17,8 @@ constexpr int kMaxDims = 6;
 constexpr int kMaxFused = 128;       // tensors fused into one response
 constexpr int kReqRing = 256;        // outstanding requests per rank
 constexpr int kRespRing = 64;        // outstanding responses
+constexpr int kCacheWords = 16;      // response cache: 64 * kCacheWords entries, one announce bit each
+constexpr int kCacheBits = 64 * kCacheWords;
 
 enum DType : uint32_t {
   kU8 = 0, kI8 = 1, kI32 = 2, kI64 = 3, kF16 = 4, kBF16 = 5, kF32 = 6, kF64 = 7, kBool = 8,
@@ -66,6 +68,8 @@ struct Response {
   double postscale;
   int32_t last_joined;                   // kJoin: rank that joined last
   uint32_t has_error;
+  uint32_t cacheable;                    // every rank may insert these names into its response cache
+  uint32_t from_cache;                   // agreed through the announce bitmask, not through request records
   char error[512];
   int64_t numel[kMaxFused];              // per tensor element count (joined ranks need it)
   int64_t dim0[kMaxRanks];               // allgather: first-dim size per rank

@@ -284,6 +284,18 @@ void Engine::publish_local() {
         queue_.pop_front();
         continue;
       }
+      const int cid = cache_enabled_ ? cache_lookup(e.req) : -1;
+      if (cid >= 0) {
+        // steady state: this exact (name, type, dtype, shape, op, scales) was negotiated before - announce it with
+        // one bit; the coordinator ANDs the bit rows of all ranks
+        hdr->cache_bits[opt_.rank][cid >> 6].fetch_or(1ull << (cid & 63), std::memory_order_release);
+        cache_hits_.fetch_add(1, std::memory_order_relaxed);
+        pending_.emplace(name, e);
+        queue_.pop_front();
+        wrote = true;
+        continue;
+      }
+      if (e.req.type == kAllreduce || e.req.type == kBroadcast) cache_misses_.fetch_add(1, std::memory_order_relaxed);
       uint64_t head = ring.head.load(std::memory_order_relaxed);
       uint64_t tail = ring.tail.load(std::memory_order_acquire);
       if (head - tail >= (uint64_t)kReqRing) break;  // coordinator is behind: retry next cycle
@@ -297,6 +309,39 @@ void Engine::publish_local() {
   }
   for (auto& f : failed) complete_handle(f.first, f.second);
   if (wrote && opt_.rank != 0) shm_.ring_doorbell();
+}
+
+static bool same_signature(const Request& a, const Request& b) {
+  if (a.type != b.type || a.dtype != b.dtype || (a.device < 0) != (b.device < 0) || a.op != b.op || a.root != b.root ||
+      a.ndim != b.ndim || a.prescale != b.prescale || a.postscale != b.postscale)
+    return false;
+  for (uint32_t i = 0; i < a.ndim; ++i)
+    if (a.shape[i] != b.shape[i]) return false;
+  return true;
+}
+
+// id of the cache entry that `r` may be announced through, or -1
+int Engine::cache_lookup(const Request& r) {
+  if (r.type != kAllreduce && r.type != kBroadcast) return -1;
+  auto it = cache_index_.find(r.name);
+  if (it == cache_index_.end()) return -1;
+  return same_signature(cache_[it->second], r) ? it->second : -1;
+}
+
+// Called by every rank while executing a cacheable response (same order everywhere => same ids everywhere).
+void Engine::cache_insert(const Response& r, const std::vector<Entry*>& es) {
+  for (uint32_t k = 0; k < r.n; ++k) {
+    if (!es[k]) continue;   // cannot happen for cacheable responses (no rank had joined)
+    auto it = cache_index_.find(r.names[k]);
+    if (it != cache_index_.end()) {
+      cache_[it->second] = es[k]->req;          // signature changed: same id, new signature, on every rank
+      if (opt_.rank == 0 && (size_t)it->second < demoted_.size()) demoted_[it->second] = 0;
+      continue;
+    }
+    if ((int)cache_.size() >= kCacheBits) continue;
+    cache_index_.emplace(r.names[k], (int)cache_.size());
+    cache_.push_back(es[k]->req);
+  }
 }
 
 static std::string shape_str(const Request& r) {
@@ -319,6 +364,15 @@ void Engine::absorb(int src, const Request& r) {
   std::string name(r.name);
   auto it = table_.find(name);
   const int world = opt_.world;
+  {
+    // a rank announced a cached name with a full record (its signature changed): the other ranks' bits for that id
+    // are folded into the record path until the next response re-establishes the entry
+    auto ci = cache_index_.find(name);
+    if (ci != cache_index_.end()) {
+      if (demoted_.size() < cache_.size()) demoted_.resize(cache_.size(), 0);
+      demoted_[ci->second] = 1;
+    }
+  }
   if (it == table_.end()) {
     Record rec;
     rec.first = r;
@@ -384,7 +438,97 @@ void Engine::coordinate() {
     }
     ring.tail.store(tail, std::memory_order_release);
   }
+  emit_cached();
   emit_ready();
+}
+
+// Response-cache fast path (coordinator): swap the announce words out of shared memory, OR them into the per-rank
+// accumulators, AND the rows; every id whose bit survives is ready on all ranks.  Ready ids are emitted in id order,
+// consecutive compatible allreduces fused exactly like the record path does.
+void Engine::emit_cached() {
+  if (cache_.empty()) return;
+  ShmHeader* hdr = shm_.hdr();
+  const int world = opt_.world;
+  const int words = ((int)cache_.size() + 63) / 64;
+  bool any = false;
+  for (int r = 0; r < world; ++r)
+    for (int w = 0; w < words; ++w) {
+      if (hdr->cache_bits[r][w].load(std::memory_order_relaxed) == 0) continue;
+      const uint64_t b = hdr->cache_bits[r][w].exchange(0, std::memory_order_acq_rel);
+      acc_bits_[r][w] |= b;
+      any = any || b != 0;
+    }
+  if (demoted_.size() < cache_.size()) demoted_.resize(cache_.size(), 0);
+  if (cache_first_us_.size() < cache_.size()) cache_first_us_.resize(cache_.size(), 0);
+  // ranks that joined, or ids demoted to the record path: hand the accumulated announcements to absorb()
+  for (int w = 0; w < words; ++w)
+    for (int r = 0; r < world; ++r) {
+      uint64_t b = acc_bits_[r][w];
+      while (b) {
+        const int bit = __builtin_ctzll(b);
+        b &= b - 1;
+        const int id = w * 64 + bit;
+        if (joined_mask_ != 0 || demoted_[id]) {
+          acc_bits_[r][w] &= ~(1ull << bit);
+          absorb(r, cache_[id]);
+        } else if (cache_first_us_[id] == 0) {
+          cache_first_us_[id] = mono_us();
+        }
+      }
+    }
+  if (!any && joined_mask_ == 0) {
+    bool pending = false;
+    for (int w = 0; w < words && !pending; ++w) pending = acc_bits_[0][w] != 0;
+    if (!pending) return;
+  }
+  std::unique_ptr<Response> resp(new Response);
+  std::vector<int> ready;
+  for (int w = 0; w < words; ++w) {
+    uint64_t m = ~0ull;
+    for (int r = 0; r < world; ++r) m &= acc_bits_[r][w];
+    while (m) {
+      const int bit = __builtin_ctzll(m);
+      m &= m - 1;
+      ready.push_back(w * 64 + bit);
+    }
+  }
+  size_t i = 0;
+  while (i < ready.size()) {
+    const Request& f = cache_[ready[i]];
+    Response& r = *resp;
+    memset(&r, 0, offsetof(Response, numel));
+    r.type = f.type; r.dtype = f.dtype; r.device = f.device; r.op = f.op; r.root = f.root;
+    r.prescale = f.prescale; r.postscale = f.postscale; r.last_joined = -1;
+    r.cacheable = 1; r.from_cache = 1;
+    r.n = 1;
+    snprintf(r.names[0], kMaxName, "%s", f.name);
+    auto numel_of_req = [](const Request& q) { int64_t n = 1; for (uint32_t d = 0; d < q.ndim; ++d) n *= q.shape[d]; return n; };
+    r.numel[0] = numel_of_req(f);
+    size_t consumed = 1;
+    if (f.type == kAllreduce) {
+      int64_t bytes = r.numel[0] * (int64_t)dtype_size(f.dtype);
+      while (i + consumed < ready.size() && r.n < (uint32_t)kMaxFused) {
+        const Request& g = cache_[ready[i + consumed]];
+        if (g.type != kAllreduce || g.dtype != f.dtype || g.device != f.device || g.op != f.op ||
+            g.prescale != f.prescale || g.postscale != f.postscale)
+          break;
+        const int64_t nb = numel_of_req(g) * (int64_t)dtype_size(g.dtype);
+        if (bytes + nb > opt_.fusion_threshold) break;
+        snprintf(r.names[r.n], kMaxName, "%s", g.name);
+        r.numel[r.n] = numel_of_req(g);
+        bytes += nb;
+        ++r.n;
+        ++consumed;
+      }
+    }
+    for (size_t k = 0; k < consumed; ++k) {
+      const int id = ready[i + k];
+      for (int q = 0; q < world; ++q) acc_bits_[q][id >> 6] &= ~(1ull << (id & 63));
+      cache_first_us_[id] = 0;
+    }
+    publish(&r);
+    i += consumed;
+  }
 }
 
 static int64_t numel_of(const Request& r) {
@@ -417,6 +561,7 @@ void Engine::emit_ready() {
     r.postscale = f.postscale;
     r.last_joined = -1;
     r.n = 1;
+    r.cacheable = (joined_mask_ == 0 && (f.type == kAllreduce || f.type == kBroadcast)) ? 1 : 0;
     snprintf(r.names[0], kMaxName, "%s", f.name);
     r.numel[0] = numel_of(f);
     if (rec.error.empty() && joined_mask_ != 0 && f.type != kAllreduce && f.type != kBarrier)
@@ -454,7 +599,11 @@ void Engine::emit_ready() {
       if (f.type == kAlltoall)
         for (int k = 0; k < world * world; ++k) r.splits[k] = rec.splits[k];
     }
-    for (size_t k = 0; k < consumed; ++k) table_.erase(ready[i + k]);
+    for (size_t k = 0; k < consumed; ++k) {
+      auto ci = cache_index_.find(ready[i + k]->first);
+      if (ci != cache_index_.end() && (size_t)ci->second < demoted_.size()) demoted_[ci->second] = 0;
+      table_.erase(ready[i + k]);
+    }
     publish(&r);
     i += consumed;
   }
@@ -504,6 +653,17 @@ void Engine::check_stalls() {
   if (opt_.stall_warn_s <= 0 && opt_.stall_shutdown_s <= 0) return;
   const uint64_t now = mono_us();
   const int world = opt_.world;
+  for (size_t id = 0; id < cache_first_us_.size(); ++id) {
+    if (cache_first_us_[id] == 0) continue;
+    const double age = (now - cache_first_us_[id]) * 1e-6;
+    const double limit = opt_.stall_shutdown_s > 0 ? opt_.stall_shutdown_s : opt_.stall_warn_s;
+    if (limit > 0 && age > limit) {
+      // hand a stuck cached announcement to the record path: it carries the warnings / shutdown logic
+      if (demoted_.size() < cache_.size()) demoted_.resize(cache_.size(), 0);
+      demoted_[id] = 1;
+      cache_first_us_[id] = 0;
+    }
+  }
   const uint64_t full = world == 64 ? ~0ull : ((1ull << world) - 1);
   for (auto& kv : table_) {
     Record& rec = kv.second;
@@ -567,11 +727,17 @@ void Engine::execute(const Response& r) {
     for (uint32_t k = 0; k < r.n; ++k)
       timeline_.event(r.names[k], (std::string("NEGOTIATE_") + type_name(r.type)).c_str(), 'E', t0);
 
+  for (auto* e : es)
+    if (e && e->enqueue_us) {
+      neg_us_sum_.fetch_add(t0 - e->enqueue_us, std::memory_order_relaxed);
+      neg_count_.fetch_add(1, std::memory_order_relaxed);
+    }
   if (r.has_error) {
     for (auto* e : es)
       if (e) complete(e, r.error);
     return;
   }
+  if (r.cacheable && cache_enabled_) cache_insert(r, es);
   const int world = opt_.world, rank = opt_.rank;
   const int64_t esz = (int64_t)dtype_size(r.dtype);
   std::string err;

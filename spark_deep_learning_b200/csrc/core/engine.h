@@ -86,6 +86,11 @@ class Engine {
   int world() const { return opt_.world; }
   uint64_t responses_executed() const { return responses_executed_; }
   uint64_t tensors_fused() const { return tensors_fused_; }
+  uint64_t cache_hits() const { return cache_hits_; }
+  uint64_t cache_misses() const { return cache_misses_; }
+  uint64_t cache_size() const { return cache_.size(); }
+  double negotiation_us() const { return neg_count_ ? (double)neg_us_sum_ / (double)neg_count_ : 0.0; }
+  void set_cache_enabled(bool on) { cache_enabled_ = on; }
 
  private:
   struct Record {
@@ -103,6 +108,9 @@ class Engine {
   void coordinate();
   void absorb(int src, const Request& r);
   void emit_ready();
+  void emit_cached();
+  void cache_insert(const Response& r, const std::vector<Entry*>& es);
+  int cache_lookup(const Request& r);
   void publish(Response* r);
   void check_stalls();
   bool consume_responses();
@@ -133,6 +141,16 @@ class Engine {
   std::vector<uint8_t> fuse_buf_;
   Timeline timeline_;
   uint64_t responses_executed_ = 0, tensors_fused_ = 0;
+  // response cache (identical on every rank: entries are inserted while executing responses, which all ranks see in
+  // the same order)
+  std::vector<Request> cache_;
+  std::unordered_map<std::string, int> cache_index_;
+  bool cache_enabled_ = true;
+  std::atomic<uint64_t> cache_hits_{0}, cache_misses_{0}, neg_us_sum_{0}, neg_count_{0};
+  // coordinator side of the fast path
+  uint64_t acc_bits_[kMaxRanks][kCacheWords] = {};
+  std::vector<uint8_t> demoted_;          // cache ids that must go through the record path until their next response
+  std::vector<uint64_t> cache_first_us_;  // stall reporting
 };
 
 }  // namespace sdl

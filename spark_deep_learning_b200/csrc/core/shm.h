@@ -40,6 +40,9 @@ struct ShmHeader {
   ShmBarrier barriers[4];              // [0] data plane, [1] init/shutdown, [2..3] spare
   std::atomic<uint64_t> resp_head;     // responses published so far
   std::atomic<uint64_t> resp_tail[kMaxRanks];
+  // response cache fast path: rank r announces "my cached tensor #i is ready" by setting bit i of its row; the
+  // coordinator swaps the words out and ANDs the rows - no request record, no string handling
+  std::atomic<uint64_t> cache_bits[kMaxRanks][kCacheWords];
   RankRing rings[kMaxRanks];
   Response resp[kRespRing];
 };

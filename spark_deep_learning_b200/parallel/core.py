@@ -67,6 +67,13 @@ def load():
         lib.sdl_timeline_stop.argtypes = [vp]
     if hasattr(lib, "sdl_gbdt_hist_cpu"):          # absent only in a stale in-tree build
         lib.sdl_gbdt_hist_cpu.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32]
+    if hasattr(lib, "sdl_stat_cache_hits"):
+        for fn in ("sdl_stat_cache_hits", "sdl_stat_cache_misses", "sdl_stat_cache_size"):
+            getattr(lib, fn).restype = u64
+            getattr(lib, fn).argtypes = [vp]
+        lib.sdl_stat_negotiation_us.restype = dbl
+        lib.sdl_stat_negotiation_us.argtypes = [vp]
+        lib.sdl_set_cache_enabled.argtypes = [vp, i32]
     if hasattr(lib, "sdl_exit_watchdog"):
         lib.sdl_exit_watchdog.argtypes = [dbl, i32]
         lib.sdl_exit_watchdog.restype = None
@@ -77,6 +84,13 @@ def load():
 def exit_watchdog(seconds, code):
     """Native detached thread that ``_exit(code)``s after ``seconds`` unless the process has left by itself."""
     lib = load()
+    if hasattr(lib, "sdl_stat_cache_hits"):
+        for fn in ("sdl_stat_cache_hits", "sdl_stat_cache_misses", "sdl_stat_cache_size"):
+            getattr(lib, fn).restype = u64
+            getattr(lib, fn).argtypes = [vp]
+        lib.sdl_stat_negotiation_us.restype = dbl
+        lib.sdl_stat_negotiation_us.argtypes = [vp]
+        lib.sdl_set_cache_enabled.argtypes = [vp, i32]
     if hasattr(lib, "sdl_exit_watchdog"):
         lib.sdl_exit_watchdog(float(seconds), int(code))
 
@@ -159,8 +173,18 @@ class CoreEngine(object):
         self._lib.sdl_set_gpu_executor(self._e, ctypes.c_void_p(fn_addr), ctypes.c_void_p(ctx_addr))
 
     def stats(self):
-        return {"responses": self._lib.sdl_stat_responses(self._e),
-                "tensors": self._lib.sdl_stat_tensors(self._e)}
+        out = {"responses": self._lib.sdl_stat_responses(self._e),
+               "tensors": self._lib.sdl_stat_tensors(self._e)}
+        if hasattr(self._lib, "sdl_stat_cache_hits"):
+            out.update({"cache_hits": self._lib.sdl_stat_cache_hits(self._e),
+                        "cache_misses": self._lib.sdl_stat_cache_misses(self._e),
+                        "cache_size": self._lib.sdl_stat_cache_size(self._e),
+                        "negotiation_us": self._lib.sdl_stat_negotiation_us(self._e)})
+        return out
+
+    def set_cache_enabled(self, on):
+        if hasattr(self._lib, "sdl_set_cache_enabled"):
+            self._lib.sdl_set_cache_enabled(self._e, 1 if on else 0)
 
     def timeline_start(self, path):
         return self._lib.sdl_timeline_start(self._e, path.encode()) == 0

@@ -92,6 +92,7 @@ def init(comm=None, process_sets=None):  # pylint: disable=unused-argument
         else:
             shm_name = ctx.store.get("shm_name", cfg.start_timeout_s)
         _S.engine = _core.CoreEngine(shm_name, ctx.rank, ctx.size, cfg)
+        _S.engine.set_cache_enabled(bool(getattr(cfg, "response_cache", True)))
         _S.ctx, _S.cfg = ctx, cfg
         _S.counters = {}
         if use_cuda:
@@ -233,7 +234,9 @@ def comm_backend():
 
 
 def engine_stats():
-    """Counters of the C++ engine (responses, fused tensors, stall warnings, ...) as a dict."""
+    """Counters of the C++ engine as a dict: ``responses`` executed, ``tensors`` fused into them, response-cache
+    ``cache_hits`` / ``cache_misses`` / ``cache_size`` (collectives announced with one bit instead of a request record)
+    and ``negotiation_us`` (mean time from ``enqueue`` to the agreed response on this rank)."""
     _require()
     return _S.engine.stats()
 

@@ -39,6 +39,9 @@ class Config(object):
             ["SPARKDL_STALL_SHUTDOWN_TIME_SECONDS", "HOROVOD_STALL_SHUTDOWN_TIME_SECONDS"],
             0.0, float)
         self.autotune = _env(["SPARKDL_AUTOTUNE", "HOROVOD_AUTOTUNE"], False, _bool)
+        # response cache: repeated (name, shape, dtype, op) collectives are announced with one bit (0 disables, like
+        # HOROVOD_CACHE_CAPACITY=0)
+        self.response_cache = _env(["SPARKDL_RESPONSE_CACHE", "HOROVOD_CACHE_CAPACITY"], 1024, int) > 0
         # --- CPU shared-memory data plane --------------------------------------------------
         self.shm_stage_bytes = _env(["SPARKDL_SHM_STAGE_BYTES"], 8 << 20, int)
         # --- GPU collectives ---------------------------------------------------------------

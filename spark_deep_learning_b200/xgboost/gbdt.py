@@ -512,8 +512,10 @@ def _cuda_lib():
                                         ctypes.c_float, ctypes.c_uint)
         lib.sdlc_gbdt_hist.restype = i32
         lib.sdlc_gbdt_hist.argtypes = [vp, vp, vp, vp, i64, i32, u64]
+        lib.sdlc_gbdt_hist_smem.restype = i32
+        lib.sdlc_gbdt_hist_smem.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, u64]
         lib.sdlc_gbdt_hist_allreduce.restype = i32
-        lib.sdlc_gbdt_hist_allreduce.argtypes = [vp, i32, i32, vp, vp, vp, i64, i32, i64, vp, u32, u64]
+        lib.sdlc_gbdt_hist_allreduce.argtypes = [vp, i32, i32, vp, vp, i64, vp, vp, i64, i32, i32, i64, vp, u32, u64]
         lib.sdlc_gbdt_predict.restype = i32
         lib.sdlc_gbdt_predict.argtypes = [vp, i64, i32, f32, i32] + [vp] * 8 + [i32, i32, vp, u64]
         _LIB_SIG = True
@@ -635,6 +637,12 @@ class _HistBuilder(object):
         self.grid_ctr = None
         self.grid_epoch = 0
         self.launches = 0
+        # feature-major copy of the bins for the shared-memory privatised build (coalesced per-feature loads)
+        self.binsT, self.pitch = None, 0
+        if self.cuda and os.environ.get("SPARKDL_GBDT_SMEM_HIST", "1") != "0":
+            self.pitch = (self.n + 15) // 16 * 16
+            self.binsT = torch.zeros(self.F, self.pitch, dtype=torch.uint8, device=bins.device)
+            self.binsT[:, :self.n] = bins.t()
         if self.cuda and dist.size > 1 and use_fused:
             self.comm = dist.hvd.comm_backend()   # None on a CPU-only gang -> generic allreduce path
 
@@ -657,8 +665,9 @@ class _HistBuilder(object):
                 hist = sym.tensor(torch.int64, nelem)
                 hist.zero_()
                 self.grid_epoch += 1
-                rc = lib.sdlc_gbdt_hist_allreduce(self.comm._h, 2, sym.id, _vp(self.bins), _vp(gh_q), _vp(pos), self.n, self.F,
-                                                  nelem, _vp(self.grid_ctr), self.grid_epoch, stream)
+                rc = lib.sdlc_gbdt_hist_allreduce(self.comm._h, 2, sym.id, _vp(self.bins),
+                                                  _vp(self.binsT) if self.binsT is not None else None, self.pitch, _vp(gh_q), _vp(pos),
+                                                  self.n, self.F, n_nodes, nelem, _vp(self.grid_ctr), self.grid_epoch, stream)
                 if rc < 0:
                     raise RuntimeError("gbdt_hist_allreduce failed: %s" % self.comm._err())
                 # the device-local barrier counts `rc` CTAs per launch
@@ -666,7 +675,12 @@ class _HistBuilder(object):
                 self.launches += 1
                 return hist.view(n_nodes, self.F, MAX_BINS, 2).clone()
             hist = torch.zeros(nelem, dtype=torch.int64, device=self.bins.device)
-            if lib.sdlc_gbdt_hist(_vp(self.bins), _vp(gh_q), _vp(pos), _vp(hist), self.n, self.F, stream) != 0:
+            rc = 1
+            if self.binsT is not None:
+                rc = lib.sdlc_gbdt_hist_smem(_vp(self.binsT), self.pitch, _vp(gh_q), _vp(pos), _vp(hist), self.n, self.F, n_nodes, stream)
+                if rc < 0:
+                    raise RuntimeError("sdlc_gbdt_hist_smem failed")
+            if rc == 1 and lib.sdlc_gbdt_hist(_vp(self.bins), _vp(gh_q), _vp(pos), _vp(hist), self.n, self.F, stream) != 0:
                 raise RuntimeError("sdlc_gbdt_hist failed")
             self.launches += 1
             from spark_deep_learning_b200.utils import launch_counter

@@ -29,6 +29,30 @@ def test_gpu_training_matches_cpu():
     assert np.sqrt(np.mean((pg - y) ** 2)) < 0.6 * y.std()
 
 
+@pytest.mark.parametrize("n,f,nodes", [(50000, 12, 1), (200001, 64, 32), (70000, 7, 48), (30000, 20, 64)])
+def test_hist_kernels_bit_exact(n, f, nodes, monkeypatch):
+    """shared-memory privatised histogram == global-atomic histogram == an index_add reference, bit for bit
+    (nodes=64 exceeds the shared-memory tiling and must fall back silently)."""
+    import torch
+    from spark_deep_learning_b200.xgboost import gbdt
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(n)
+    bins = torch.randint(0, 256, (n, f), device=dev, dtype=torch.uint8, generator=g)
+    gh = torch.randint(-2 ** 30, 2 ** 30, (n, 2), device=dev, dtype=torch.int32, generator=g)
+    pos = torch.randint(-1, nodes, (n,), device=dev, dtype=torch.int32, generator=g)
+    ref = torch.zeros(nodes * f * 256, 2, dtype=torch.int64, device=dev)
+    live = pos >= 0
+    idx = (pos.long()[:, None] * f + torch.arange(f, device=dev)[None, :]) * 256 + bins.long()
+    ref.index_add_(0, idx[live].reshape(-1), gh.long()[live][:, None, :].expand(-1, f, -1).reshape(-1, 2))
+    out = {}
+    for smem in ("1", "0"):
+        monkeypatch.setenv("SPARKDL_GBDT_SMEM_HIST", smem)
+        b = gbdt._HistBuilder(bins, gbdt._Dist(), use_fused=False)
+        assert (b.binsT is not None) == (smem == "1")
+        out[smem] = b.build(gh, pos, nodes).reshape(-1, 2).clone()
+    assert torch.equal(out["1"], ref) and torch.equal(out["0"], ref)
+
+
 @pytest.mark.multigpu
 def test_distributed_gpu_fused_hist_allreduce():
     from sparkdl.xgboost import XgboostRegressor

@@ -573,3 +573,95 @@ def test_shutdown_then_init_in_the_same_job():
         return out
     res = HorovodRunner(np=-2).run(main)
     assert res == [1.0, 3.0, 5.0]
+
+
+def _cache_main():
+    import time
+    import torch
+    import sparkdl.hvd as hvd
+    hvd.init()
+    r, n = hvd.rank(), hvd.size()
+    names = ["w%d" % i for i in range(12)]
+    res = {"ok": True, "why": []}
+    for step in range(6):
+        # every rank submits in its own order (negotiation must still agree on one global order)
+        order = list(range(len(names)))
+        if r % 2 == 1:
+            order.reverse()
+        if step % 2 == 1:
+            order = order[3:] + order[:3]
+        if r == n - 1:
+            time.sleep(0.01)
+        ts = {i: torch.full((5 + i,), float(r + step + i)) for i in order}
+        hs = {i: hvd.allreduce_async_(ts[i], op=hvd.Sum, name=names[i]) for i in order}
+        for i in order:
+            hvd.synchronize(hs[i])
+            exp = float(sum(q + step + i for q in range(n)))
+            if ts[i][0].item() != exp:
+                res["ok"] = False
+                res["why"].append((step, i, ts[i][0].item(), exp))
+        b = torch.full((7,), float(r))
+        hvd.broadcast_(b, root_rank=step % n, name="bcast")
+        if b[0].item() != float(step % n):
+            res["ok"] = False
+            res["why"].append(("bcast", step, b[0].item()))
+    st1 = hvd.engine_stats()
+    # a signature change (new shape under an old name) must renegotiate, then be cached again
+    for step in range(3):
+        t = torch.full((3, 4), float(r + 1))
+        hvd.allreduce_(t, op=hvd.Sum, name="w0")
+        if t[0, 0].item() != float(n * (n + 1) // 2):
+            res["ok"] = False
+            res["why"].append(("reshape", step, t[0, 0].item()))
+    st2 = hvd.engine_stats()
+    # ragged allgather (not cacheable) keeps working next to cached names
+    g = hvd.allgather(torch.full((r + 1, 2), float(r)), name="ag")
+    res["ag"] = g.shape[0]
+    # join: cached tensors of the ranks that are still training are completed with zeros from the joined ranks
+    if r == 0:
+        last = hvd.join()
+    else:
+        t = torch.full((5,), 2.0)
+        hvd.allreduce_(t, op=hvd.Sum, name="w0j")
+        t2 = torch.full((3, 4), 1.0)
+        hvd.allreduce_(t2, op=hvd.Sum, name="w0")      # cached name while rank 0 has joined
+        res["join_sum"] = (t[0].item(), t2[0, 0].item())
+        last = hvd.join()
+    res["stats1"], res["stats2"] = st1, st2
+    hvd.shutdown()
+    return res if r != 0 else dict(res, rank0=True)
+
+
+def test_response_cache_bitmask_fast_path():
+    """repeated (name, shape, dtype) collectives are agreed through the shared-memory announce bitmask;
+    out-of-order submission, a signature change, ragged allgather next to cached names, and join all still work."""
+    import os
+    os.environ["SPARKDL_NUM_GPUS"] = "0"
+    try:
+        res = HorovodRunner(np=-3).run(_cache_main)
+    finally:
+        del os.environ["SPARKDL_NUM_GPUS"]
+    assert res["ok"], res["why"]
+    s1, s2 = res["stats1"], res["stats2"]
+    assert s1["cache_size"] == 13 and s1["cache_hits"] >= 5 * 13 - 13       # everything after the first step is a hit
+    assert s1["negotiation_us"] > 0
+    assert s2["cache_misses"] == s1["cache_misses"] + 1 and s2["cache_hits"] == s1["cache_hits"] + 2
+    assert res["ag"] == 6
+
+
+def test_response_cache_can_be_disabled(monkeypatch):
+    monkeypatch.setenv("SPARKDL_NUM_GPUS", "0")
+    monkeypatch.setenv("SPARKDL_RESPONSE_CACHE", "0")
+
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        for _ in range(4):
+            t = torch.ones(8)
+            hvd.allreduce_(t, op=hvd.Sum, name="x")
+        st = hvd.engine_stats()
+        hvd.shutdown()
+        return st, float(t[0])
+    st, v = HorovodRunner(np=-2).run(main)
+    assert st["cache_hits"] == 0 and v == 2.0
