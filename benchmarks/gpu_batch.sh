@@ -26,6 +26,7 @@ for stage in "$@"; do
     probes)    (timeout 300 python benchmarks/resnet_probe.py 2>&1 | tail -30) > gpurun_out/resnet_probe.txt
                (timeout 300 python benchmarks/bert_probe.py 2>&1 | tail -30) > gpurun_out/bert_probe.txt
                tail -12 gpurun_out/resnet_probe.txt gpurun_out/bert_probe.txt ;;
+    xgbprof)   (XGB_PROFILE=gpurun_out/xgb_profile.txt XGB_BENCH_SKLEARN=0 timeout 400 python benchmarks/xgboost_bench.py --np 1 2>&1 | tail -3) > gpurun_out/xgb_prof.log; cat gpurun_out/xgb_prof.log; cut -c1-200 gpurun_out/xgb_profile.txt | head -80 ;;
     xgb)       NPX=${XGB_NP:-1}; (timeout 300 python -m pytest tests/test_gpu_xgboost.py -q -m gpu 2>&1 | tail -5) > gpurun_out/pytest_xgb.txt; cat gpurun_out/pytest_xgb.txt
                (timeout 400 python benchmarks/xgboost_bench.py --np $NPX --out gpurun_out/xgboost_bench_np$NPX.json 2>&1 | tail -4) > gpurun_out/xgb_np$NPX.txt; cat gpurun_out/xgb_np$NPX.txt
                (SPARKDL_GBDT_SMEM_HIST=0 timeout 400 python benchmarks/xgboost_bench.py --np $NPX --out gpurun_out/xgboost_bench_np${NPX}_globalatomics.json 2>&1 | tail -2) > gpurun_out/xgb_np${NPX}_ga.txt; cat gpurun_out/xgb_np${NPX}_ga.txt ;;
