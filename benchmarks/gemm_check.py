@@ -44,6 +44,13 @@ def case_fwd():
                 ref = ref_pre if act is None else torch.nn.functional.gelu(
                     ref_pre, approximate="tanh" if act == "gelu_tanh" else "none")
                 report("fwd m%d n%d k%d act=%s bn=%d" % (m, n, k, act, bn), [rel(y, ref), rel(pre, ref_pre)])
+                if act is not None:
+                    # second output = act'(z) instead of z (what the backward pass multiplies by)
+                    y3, der = gemm.gemm_bf16(x, w, b, act, save_pre_act=True, block_n=bn, save_deriv=True)
+                    torch.cuda.synchronize()
+                    z = ref_pre.clone().requires_grad_(True)
+                    torch.nn.functional.gelu(z, approximate="tanh" if act == "gelu_tanh" else "none").sum().backward()
+                    report("fwd+deriv m%d n%d k%d act=%s bn=%d" % (m, n, k, act, bn), [rel(y3, ref), rel(der, z.grad)])
                 if act is None and bn == 256:
                     y2, _ = gemm.gemm_bf16(x, w, None, None, block_n=0)
                     torch.cuda.synchronize()
@@ -64,6 +71,13 @@ def case_bwd():
             z = pre.float().requires_grad_(True)
             torch.nn.functional.gelu(z, approximate="tanh" if act == "gelu_tanh" else "none").sum().backward()
             report("dgrad+dgelu(%s) m%d nout%d kin%d" % (act, m, n_out, k_in), [rel(dz, (dy.float() @ w.float()) * z.grad)])
+        der = rnd(m, k_in, scale=0.5)
+        dz = gemm.dgrad(dy, w, der, "deriv")
+        g2 = gemm.gelu_bwd(dy[:, :min(n_out, k_in)].contiguous(), der[:, :min(n_out, k_in)].contiguous(), "deriv")
+        torch.cuda.synchronize()
+        report("dgrad*deriv m%d nout%d kin%d" % (m, n_out, k_in),
+               [rel(dz, (dy.float() @ w.float()) * der.float()),
+                rel(g2, dy[:, :min(n_out, k_in)].float() * der[:, :min(n_out, k_in)].float())])
 
 
 def case_wgrad():

@@ -48,6 +48,26 @@ for stage in "$@"; do
     gemmlab)   for d in 0 1 2 3 4; do (SPARKDL_GEMM_DBG=$d timeout 120 python benchmarks/gemm_lab.py 2>&1 | grep -v cublas | tail -8); done > gpurun_out/gemm_lab.txt
                (timeout 120 python benchmarks/gemm_lab.py 2>&1 | grep cublas) >> gpurun_out/gemm_lab.txt; cat gpurun_out/gemm_lab.txt ;;
     gemmncu)   timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -c 6 -f -o gpurun_out/prof_gemm2 python benchmarks/gemm_lab.py ncu > gpurun_out/ncu_gemm2.log 2>&1; tail -3 gpurun_out/ncu_gemm2.log ;;
+    ncuall)    # one --set full capture per hot kernel family (B200_PROFILING.md recipe); reports -> gpurun_out/r2_*.ncu-rep
+               NCU="ncu --set full --clock-control none --import-source on -f"
+               timeout 400 $NCU -k regex:gemm_kernel -s 3 -c 5 -o gpurun_out/r2_gemm python benchmarks/ncu_targets.py gemm > gpurun_out/ncu_r2_gemm.log 2>&1; tail -1 gpurun_out/ncu_r2_gemm.log
+               timeout 300 $NCU -k regex:"bn_|maxpool|stem" -s 12 -c 6 -o gpurun_out/r2_bn python benchmarks/ncu_targets.py bn > gpurun_out/ncu_r2_bn.log 2>&1; tail -1 gpurun_out/ncu_r2_bn.log
+               timeout 300 $NCU -k regex:"ln_" -s 6 -c 3 -o gpurun_out/r2_ln python benchmarks/ncu_targets.py ln > gpurun_out/ncu_r2_ln.log 2>&1; tail -1 gpurun_out/ncu_r2_ln.log
+               timeout 300 $NCU -k regex:"maxpool" -s 4 -c 2 -o gpurun_out/r2_pool python benchmarks/ncu_targets.py pool > gpurun_out/ncu_r2_pool.log 2>&1; tail -1 gpurun_out/ncu_r2_pool.log
+               timeout 300 $NCU -k regex:"xent" -s 2 -c 2 -o gpurun_out/r2_xent python benchmarks/ncu_targets.py xent > gpurun_out/ncu_r2_xent.log 2>&1; tail -1 gpurun_out/ncu_r2_xent.log
+               timeout 300 $NCU -k regex:"stem_s2d" -s 1 -c 1 -o gpurun_out/r2_stem python benchmarks/ncu_targets.py stem > gpurun_out/ncu_r2_stem.log 2>&1; tail -1 gpurun_out/ncu_r2_stem.log
+               timeout 300 $NCU -k regex:"gbdt_hist" -c 4 -o gpurun_out/r2_gbdt python benchmarks/ncu_targets.py gbdt > gpurun_out/ncu_r2_gbdt.log 2>&1; tail -1 gpurun_out/ncu_r2_gbdt.log
+               timeout 300 $NCU -k regex:"fused_step" -s 3 -c 1 -o gpurun_out/r2_fused_step python benchmarks/ncu_targets.py fused_step > gpurun_out/ncu_r2_fused_step.log 2>&1; tail -1 gpurun_out/ncu_r2_fused_step.log
+               ls -la gpurun_out/r2_*.ncu-rep ;;
+    gemmlab2)  (timeout 300 python benchmarks/gemm_lab2.py 2>&1 | tail -60) > gpurun_out/gemm_lab2.txt; cat gpurun_out/gemm_lab2.txt ;;
+    racedetail) (timeout 500 compute-sanitizer --print-limit 30 --tool racecheck python -m pytest tests/test_gpu_layernorm.py tests/test_gpu_xgboost.py -q -x -k "not distributed" 2>&1 | grep -E "=========|passed|failed" | grep -v "=========     at \|=========     in " | cut -c1-300 | tail -80) > gpurun_out/sanitizer_racecheck_ln_xent_gbdt.txt; cat gpurun_out/sanitizer_racecheck_ln_xent_gbdt.txt ;;
+    nvlink)    NPX=${NVL_NP:-2}; (timeout 300 python benchmarks/nvlink_counters.py --np $NPX --out gpurun_out/nvlink_np$NPX.json 2>&1 | tail -12) > gpurun_out/nvlink_np$NPX.txt; cat gpurun_out/nvlink_np$NPX.txt ;;
+    benchN)    N=${BENCH_NP:-2}; PORT=29611
+               for m in resnet50 bert-large; do for impl in ours reference; do
+                 PORT=$((PORT+1)); tag=$(echo $m | cut -c1-4)${N}_$impl
+                 (timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $N --steps 20 --warmup 5 --model $m --impl $impl 2> gpurun_out/$tag.err | tail -1) > gpurun_out/$tag.json; cut -c1-420 gpurun_out/$tag.json
+               done; done ;;
+    sanitize)  bash benchmarks/sanitize.sh ;;
     *)         echo "unknown stage $stage" ;;
   esac
 done

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small single-GPU drivers for `ncu` captures of our top kernels (B200_PROFILING.md recipe).
-usage: python benchmarks/ncu_targets.py gemm|bn|allreduce|fused_step"""
+usage: python benchmarks/ncu_targets.py gemm|bn|allreduce|fused_step|ln|pool|xent|stem|gbdt"""
 import ctypes
 import os
 import sys
@@ -11,18 +11,57 @@ import torch  # noqa: E402
 
 
 def gemm():
+    """One launch each of the shapes the flagship models run (fwd+GELU, dgrad, wgrad), profiler replays do the rest."""
     from spark_deep_learning_b200.ops import gemm as g
     m, n, k = 8192, 4096, 4096
     x = torch.randn(m, k, device="cuda").bfloat16()
-    w = torch.randn(n, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") * 0.05).bfloat16()
     b = torch.randn(n, device="cuda")
-    for _ in range(6):
-        g.gemm_bf16(x, w, b, "gelu", block_n=256)
-    # BERT FFN-up shape (tokens 8192, 1024 -> 4096)
-    x2 = torch.randn(8192, 1024, device="cuda").bfloat16()
-    w2 = torch.randn(4096, 1024, device="cuda").bfloat16()
-    for _ in range(6):
-        g.gemm_bf16(x2, w2, b, "gelu", block_n=256)
+    dy = torch.randn(m, n, device="cuda").bfloat16()
+    for _ in range(2):
+        g.gemm_bf16(x, w, b, "gelu")                # [8192,4096] x [4096,4096]^T + bias + GELU
+        g.dgrad(dy, w)                               # dX = dY W            (B operand MN-major)
+        g.wgrad(dy, x)                               # dW = dY^T X          (both operands MN-major, split-K)
+    # BERT-large FFN-up at the bench batch (tokens 4096, 1024 -> 4096) and the vocabulary projection
+    x2 = torch.randn(4096, 1024, device="cuda").bfloat16()
+    w2 = (torch.randn(4096, 1024, device="cuda") * 0.05).bfloat16()
+    w3 = (torch.randn(30528, 1024, device="cuda") * 0.05).bfloat16()
+    for _ in range(2):
+        g.gemm_bf16(x2, w2, b, "gelu")
+        g.gemm_bf16(x2, w3)
+    torch.cuda.synchronize()
+
+
+def xent():
+    from spark_deep_learning_b200.ops import xent as X
+    logits = torch.randn(4096, 30528, device="cuda").bfloat16().requires_grad_(True)
+    labels = torch.randint(0, 30522, (4096,), device="cuda")
+    for _ in range(3):
+        loss = X.cross_entropy(logits, labels)
+        loss.backward()
+    torch.cuda.synchronize()
+
+
+def stem():
+    from spark_deep_learning_b200.ops import pool as P
+    x = torch.randn(256, 3, 224, 224, device="cuda")
+    for _ in range(3):
+        P.stem_s2d(x)
+    torch.cuda.synchronize()
+
+
+def gbdt():
+    from spark_deep_learning_b200.xgboost import gbdt as G
+    n, f = 1000000, 64
+    bins = torch.randint(0, 256, (n, f), device="cuda", dtype=torch.uint8)
+    gh = torch.randint(-2 ** 20, 2 ** 20, (n, 2), device="cuda", dtype=torch.int32)
+    pos = torch.randint(0, 32, (n,), device="cuda", dtype=torch.int32)
+    d = G._Dist()
+    for smem in ("1", "0"):
+        os.environ["SPARKDL_GBDT_SMEM_HIST"] = smem
+        b = G._HistBuilder(bins, d, use_fused=False)
+        for _ in range(2):
+            b.build(gh, pos, 32)
     torch.cuda.synchronize()
 
 
@@ -92,4 +131,5 @@ def pool():
 
 
 if __name__ == "__main__":
-    {"gemm": gemm, "bn": bn, "allreduce": allreduce, "fused_step": fused_step, "ln": ln, "pool": pool}[sys.argv[1]]()
+    {"gemm": gemm, "bn": bn, "allreduce": allreduce, "fused_step": fused_step, "ln": ln, "pool": pool, "xent": xent,
+     "stem": stem, "gbdt": gbdt}[sys.argv[1]]()

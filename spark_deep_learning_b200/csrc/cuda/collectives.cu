@@ -714,9 +714,12 @@ int sdlc_pack(void* h, int buf, const unsigned long long* ptrs, const long long*
               int to_staging, unsigned long long stream) {
   Comm* c = static_cast<Comm*>(h);
   if (n <= 0) return 0;
-  if (n > 1024) {
-    c->last_error = "too many tensors in one pack";
-    return -1;
+  if (n > 1024) {   // the pointer table of one launch holds 1024 entries: larger batches go out as several launches
+    for (int i = 0; i < n; i += 1024) {
+      const int rc = sdlc_pack(h, buf, ptrs + i, offs + i, sizes + i, n - i < 1024 ? n - i : 1024, to_staging, stream);
+      if (rc != 0) return rc;
+    }
+    return 0;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int slot = c->table_next;

@@ -79,7 +79,7 @@ struct GemmParams {
   int splits, kb_per_split;    // split-K: number of slices / k-blocks per slice
   int m_pad;                   // split-K workspace: rows per slice (m_tiles * 256)
   int act;                     // LINEAR: 0 none, 1 GELU(tanh), 2 GELU(erf); DGELU: 1 / 2
-  int has_pre;                 // LINEAR: also store the pre-activation through map_out2
+  int has_pre;                 // LINEAR: also store through map_out2 the pre-activation (1) or act'(pre-activation) (2)
   int accumulate;              // ACC: out = dst + acc
   const void* bias;            // LINEAR: fp32 (or bf16, bias_bf16) [N] or null
   int bias_bf16;
@@ -218,29 +218,44 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float u = k0 * fmaf(k1 * x * x, x, x);
   return 0.5f * x * (1.f + tanh_approx(u));
 }
-// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution): one MUFU.EX2 + one MUFU.RCP
-__device__ __forceinline__ float fast_erf(float z) {
-  const float a = fabsf(z);
-  const float t = __fdividef(1.f, fmaf(0.3275911f, a, 1.f));
-  const float p = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  const float r = 1.f - p * __expf(-a * a);
-  return copysignf(r, z);
+// erf(x / sqrt2) as tanh of an odd polynomial: tanh(x (c1 + c3 x^2 + c5 x^4)), coefficients fitted (minimax on [0, 6]) to
+// |err| < 3.7e-5 - below MUFU.TANH's own 2^-11 and two orders below bf16 resolution.  One MUFU and 5 FP32 instructions
+// instead of the 2 MUFU + 14 of a rational erf: the epilogue of a K=1024 tile is issue-bound (8 warps do the math of
+// 32768 outputs while the tensor pipe needs only 4.4 us per tile), so the instruction count is what matters.
+// x^2 is clamped at 36: beyond it the result is +-1 anyway and the negative x^4 term must not take over.
+__device__ __forceinline__ float erf_rsqrt2(float x) {
+  const float t = fminf(x * x, 36.f);
+  return tanh_approx(x * fmaf(t, fmaf(t, -3.15807060e-4f, 3.67982560e-2f), 7.97717834e-1f));
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + fast_erf(x * 0.7071067811865476f)); }
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_rsqrt2(x), hx);
+}
+// GELU and its derivative in one go (they share the tanh; the erf form adds one MUFU.EX2 for the density)
+__device__ __forceinline__ void gelu_both(float x, int kind, float& y, float& d) {
+  if (kind == 1) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float t = tanh_approx(k0 * fmaf(k1 * x * x, x, x));
+    const float c = fmaf(0.5f, t, 0.5f);
+    y = x * c;
+    d = fmaf(0.5f * x * (1.f - t * t), k0 * fmaf(3.f * k1 * x, x, 1.f), c);
+  } else {
+    const float c = fmaf(0.5f, erf_rsqrt2(x), 0.5f);
+    y = x * c;
+    d = fmaf(x * __expf(-0.5f * x * x), 0.3989422804014327f, c);
+  }
+}
 // d/dz GELU(z)
 __device__ __forceinline__ float dgelu(float z, int kind) {
+  if (kind == 3) return z;       // the forward pass stored the derivative itself (has_pre == 2)
   if (kind == 1) {
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
     const float t = tanh_approx(k0 * fmaf(k1 * z * z, z, z));
     return 0.5f * (1.f + t) + 0.5f * z * (1.f - t * t) * k0 * fmaf(3.f * k1 * z, z, 1.f);
   }
-  // erf(z / sqrt2) = sign(z) (1 - P(t) e), t = 1 / (1 + 0.3275911 |z| / sqrt2), e = exp(-z^2 / 2): the same exponential
-  // is the Gaussian density of the second term, so one MUFU.EX2 and one MUFU.RCP serve both
-  const float a = fabsf(z) * 0.7071067811865476f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, a, 1.f));
+  // Phi(z) + z phi(z): the cdf from the tanh form above, the density from one MUFU.EX2
+  const float cdf = fmaf(0.5f, erf_rsqrt2(z), 0.5f);
   const float e = __expf(-0.5f * z * z);
-  const float pe = e * t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  const float cdf = z >= 0.f ? 1.f - 0.5f * pe : 0.5f * pe;
   return fmaf(z * e, 0.3989422804014327f, cdf);
 }
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -535,6 +550,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
         }
         if constexpr (EPI == EPI_LINEAR) {
+          if (p.has_pre == 2 && p.act != 0) {
+            // second output = act'(z): the backward dgrad epilogue then only multiplies (EPI_DGELU with act 3)
+            uint4 oy[8], od[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float y[8], d[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) gelu_both(f[8 * j + e], p.act, y[e], d[e]);
+              oy[j] = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+              od[j] = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+            }
+            store_box(od, &map_out2, col0, row0);
+            store_box(oy, &map_out, col0, row0);
+            continue;
+          }
           if (p.has_pre) store_bf16(f, &map_out2, col0, row0);
           if (p.act == 1) {
 #pragma unroll
@@ -880,7 +910,7 @@ int sdlc_gemm_ex3(const void* a, const void* a1, const void* a2, int a_part_len,
     if (a_part_len <= 0 || a_part_len * p.a_parts != split_dim || (a_part_len % (a_mn ? PAIR_M : BLOCK_K)) != 0) return -2;
   }
   p.splits = splits; p.kb_per_split = kbps; p.m_pad = m_tiles * PAIR_M;
-  p.act = act; p.has_pre = (epi == EPI_LINEAR && out2) ? 1 : 0;
+  p.act = act; p.has_pre = (epi == EPI_LINEAR && out2) ? ((act & 32) ? 2 : 1) : 0;
   p.bias = bias; p.bias_bf16 = (act & 16) ? 1 : 0; p.act = act & 15; p.aux = aux; p.ld_aux = ld_aux;
   p.accumulate = (accumulate && splits == 1) ? 1 : 0;
   if (p.accumulate && acc_epi) { p.aux = out; p.ld_aux = ld_out; }

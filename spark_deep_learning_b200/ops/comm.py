@@ -83,6 +83,7 @@ def load():
         "sdlc_check_error": (ctypes.c_uint, [vp]),
         "sdlc_clear_error": (None, [vp]),
         "sdlc_launch_count": (u64, [vp]),
+        "sdlc_max_peers": (i32, []),
         "sdlc_allreduce": (i32, [vp, i32, i32, i64, i64, i32, i32, f32, f32, i32, u64]),
         "sdlc_wire_bytes": (i64, [i64, i32]),
         "sdlc_allreduce_wire": (i32, [vp, i32, vp, i64, i32, i32, i32, i64, f32, f32, u64]),
@@ -154,7 +155,8 @@ class SymmComm(object):
         self.rank, self.world = ctx.rank, ctx.size
         self.ctx, self.cfg = ctx, cfg
         if self.world > 8:
-            raise CommError("the symmetric-memory communicator supports up to 8 GPUs on one box")
+            raise CommError("the symmetric-memory communicator supports up to 8 GPUs on one box, got world=%d "
+                            "(docs/LIMITS.md)" % self.world)
         self.device = torch.cuda.current_device() if device is None else device
         self._h = ctypes.c_void_p(self._lib.sdlc_comm_create(
             self.rank, self.world, self.device, float(cfg.kernel_timeout_ms), int(cfg.comm_ctas),
@@ -454,6 +456,8 @@ class SymmComm(object):
         if wire:
             if op not in (_core.OP_SUM, _core.OP_AVERAGE):
                 raise CommError("wire formats support sum/average only")
+            if numel % 8:
+                raise CommError("wire-format allreduce needs a multiple of 8 elements, got %d (docs/LIMITS.md)" % numel)
             if op == _core.OP_AVERAGE:
                 post = post / self.world
             wb = self._wire_buffer(buf, numel, wire)

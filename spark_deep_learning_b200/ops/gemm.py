@@ -18,7 +18,7 @@ import torch
 from spark_deep_learning_b200.ops import comm as _comm
 from spark_deep_learning_b200.utils import launch_counter
 
-ACT = {None: 0, "none": 0, "gelu_tanh": 1, "gelu": 2, "gelu_erf": 2}
+ACT = {None: 0, "none": 0, "gelu_tanh": 1, "gelu": 2, "gelu_erf": 2, "deriv": 3}   # "deriv": aux already holds act'(z)
 EPI_LINEAR, EPI_DGELU, EPI_ACC_BF16, EPI_ACC_F32, EPI_STATS = range(5)
 _sig = False
 _NUM_CLUSTERS = 74          # 148 SMs / 2
@@ -81,10 +81,11 @@ def _rowmajor(t):
 
 
 def gemm_ex(a, b, m, n, k, a_mn=False, b_mn=False, epi=EPI_ACC_BF16, out=None, out2=None, bias=None, act=None,
-            aux=None, accumulate=False, splits=1, stats=None, block_n=0):
+            aux=None, accumulate=False, splits=1, stats=None, block_n=0, out2_deriv=False):
     """Raw kernel call: ``out[m,n] = epi(A . B^T)``.  ``a`` is stored [m,k] (K-major) or [k,m] (``a_mn``); ``b`` is
     stored [n,k] or [k,n] (``b_mn``).  ``a`` may also be a tuple of 2-3 equally shaped buffers that together form A -
     split along K for a K-major A, along M for an MN-major A - so that e.g. dQ, dK, dV never have to be concatenated.
+    ``out2`` (EPI_LINEAR) receives the pre-activation, or ``act'(pre-activation)`` when ``out2_deriv``.
     Returns ``out``."""
     lib = _lib()
     parts = None
@@ -106,6 +107,8 @@ def gemm_ex(a, b, m, n, k, a_mn=False, b_mn=False, epi=EPI_ACC_BF16, out=None, o
     if splits > 1:
         ws = _workspace(dev, splits * ((m + 255) // 256) * 256 * n)
     act_code = ACT[act] if not isinstance(act, int) else act
+    if out2_deriv and out2 is not None and act_code:
+        act_code |= 32                           # out2 = act'(z) instead of z
     if bias is not None:
         if bias.dtype == torch.bfloat16 and bias.data_ptr() % 16 == 0:
             act_code |= 16                       # the epilogue reads the bf16 bias directly
@@ -127,13 +130,16 @@ def gemm_ex(a, b, m, n, k, a_mn=False, b_mn=False, epi=EPI_ACC_BF16, out=None, o
     return out
 
 
-def gemm_bf16(x2d, weight, bias=None, act=None, save_pre_act=False, block_n=None):
-    """Forward: x2d [M,K] bf16, weight [N,K] bf16, bias fp32 [N] or None -> ([M,N] bf16, pre-activation or None)."""
+def gemm_bf16(x2d, weight, bias=None, act=None, save_pre_act=False, block_n=None, save_deriv=False):
+    """Forward: x2d [M,K] bf16, weight [N,K] bf16, bias fp32 [N] or None -> ([M,N] bf16, pre-activation or None).
+    With ``save_deriv`` the second output is ``act'(pre-activation)`` (what backward needs: pass it to :func:`dgrad` /
+    :func:`gelu_bwd` with ``act="deriv"``), computed in the same epilogue where the tanh is already at hand."""
     m, k = x2d.shape
     n = weight.shape[0]
     out = torch.empty((m, n), dtype=torch.bfloat16, device=x2d.device)
     pre = torch.empty_like(out) if save_pre_act else None
-    gemm_ex(x2d, weight, m, n, k, epi=EPI_LINEAR, out=out, out2=pre, bias=bias, act=act, block_n=block_n or 0)
+    gemm_ex(x2d, weight, m, n, k, epi=EPI_LINEAR, out=out, out2=pre, bias=bias, act=act, block_n=block_n or 0,
+            out2_deriv=save_deriv)
     return out, pre
 
 
@@ -218,9 +224,10 @@ def _bias_grad(dy2d, bias, use_sink=True):
 
 
 def gelu_bwd(dy2d, pre, act):
-    """``dy2d * gelu'(pre)`` as a stand-alone pass (when the product is needed as a GEMM operand)."""
+    """``dy2d * gelu'(pre)`` as a stand-alone pass (when the product is needed as a GEMM operand); ``act="deriv"``:
+    ``pre`` already holds the derivative."""
     g = torch.empty_like(pre)
-    rc = _lib().sdlc_gelu_bwd(_p(dy2d.contiguous()), _p(pre), _p(g), pre.numel(), 1 if act == "gelu_tanh" else 2, _stream(pre))
+    rc = _lib().sdlc_gelu_bwd(_p(dy2d.contiguous()), _p(pre), _p(g), pre.numel(), ACT[act], _stream(pre))
     if rc != 0:
         raise RuntimeError("sdlc_gelu_bwd failed")
     launch_counter.add(1)
@@ -245,9 +252,9 @@ class _LinearAct(torch.autograd.Function):
         ctx.use_sink = use_sink
         x2d = x.reshape(-1, x.shape[-1])
         need_pre = act not in (None, "none") and (x.requires_grad or weight.requires_grad)
-        out, pre = gemm_bf16(x2d, weight, bias, act, save_pre_act=need_pre)
+        out, pre = gemm_bf16(x2d, weight, bias, act, save_pre_act=need_pre, save_deriv=True)   # pre = act'(z)
         ctx.save_for_backward(x2d, weight, pre, bias)
-        ctx.act = act
+        ctx.act = "deriv"
         ctx.has_bias = bias is not None
         ctx.x_shape = x.shape
         return out.view(*x.shape[:-1], weight.shape[0])
@@ -336,10 +343,10 @@ class _MLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, act):
         x2d = x.reshape(-1, x.shape[-1])
-        h, z = gemm_bf16(x2d, w1, b1, act, save_pre_act=True)
+        h, z = gemm_bf16(x2d, w1, b1, act, save_pre_act=True, save_deriv=True)     # z = act'(x W1^T + b1)
         y, _ = gemm_bf16(h, w2, b2, None)
         ctx.save_for_backward(x2d, w1, w2, z, h, b1, b2)
-        ctx.act = act
+        ctx.act = "deriv"
         ctx.x_shape = x.shape
         ctx.has_b = (b1 is not None, b2 is not None)
         return y.view(*x.shape[:-1], w2.shape[0])
@@ -348,7 +355,7 @@ class _MLP(torch.autograd.Function):
     def backward(ctx, dy):
         x2d, w1, w2, z, h, b1, b2 = ctx.saved_tensors
         dy2d, _ = _rowmajor(dy.reshape(-1, dy.shape[-1]))
-        dz = dgrad(dy2d, w2, z, ctx.act)                     # fused: (dY . W2) * gelu'(Z)
+        dz = dgrad(dy2d, w2, z, ctx.act)                     # fused: (dY . W2) * gelu'(Z), gelu'(Z) saved by forward
         grads = {}
         for name, w, g, inp in (("w2", w2, dy2d, h), ("w1", w1, dz, x2d)):
             sink = _grad_sink(w)

@@ -187,6 +187,38 @@ def test_pack_unpack_roundtrip(lib):
     vg.close()
 
 
+def test_pack_more_tensors_than_one_table(lib):
+    """2500 tensors in one call: more than the 1024-entry pointer table of a launch, so the batch goes out in slices."""
+    vg = _group(1)
+    c = vg.comms[0]
+    n = 2500
+    st = vg.alloc(n * 16)[0]
+    src = torch.arange(n * 4, device="cuda", dtype=torch.float32).reshape(n, 4)
+    dst = torch.zeros_like(src)
+    U, L = ctypes.c_ulonglong * n, ctypes.c_longlong * n
+    s = torch.cuda.current_stream().cuda_stream
+    offs, sizes = L(*[16 * i for i in range(n)]), L(*([16] * n))
+    assert lib.sdlc_pack(c._h, st.id, U(*[src[i].data_ptr() for i in range(n)]), offs, sizes, n, 1, s) == 0
+    assert lib.sdlc_pack(c._h, st.id, U(*[dst[i].data_ptr() for i in range(n)]), offs, sizes, n, 0, s) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(src, dst)
+    vg.close()
+
+
+def test_limits_are_reported_as_errors(lib):
+    """docs/LIMITS.md: more than 8 peers, a wire-format message that is not a multiple of 8 elements."""
+    from spark_deep_learning_b200.ops import comm as C
+    assert lib.sdlc_max_peers() == 8
+    assert not lib.sdlc_comm_create(0, 9, 0, 1000.0, 8, 1 << 20, 0)
+    vg = _group(2)
+    bufs = vg.alloc(1 << 12)
+    for b in bufs:
+        b.tensor(torch.float32, 1000).fill_(1.0)
+    with pytest.raises(C.CommError, match="multiple of 8"):
+        vg.comms[0].allreduce_symmetric(bufs[0], 1001, torch.float32, wire="bf16")
+    vg.close()
+
+
 @pytest.mark.parametrize("kind", ["sgd", "sgd_nesterov", "adam", "adamw"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_fused_optimizer_step_matches_torch(lib, kind, dtype):
