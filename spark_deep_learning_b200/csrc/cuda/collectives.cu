@@ -78,6 +78,59 @@ allreduce_oneshot_kernel(CollCtx c, long long nvec, int op, float pre, float pos
 }
 
 // =====================================================================================================
+// K1b  LL allreduce (<= 64 KB): no barrier at all.  Every rank pushes its vector into a receive slot of every peer as
+// {data32, flag32} pairs (64-bit stores are single-copy atomic, so a pair is never seen half-written) and spins on its
+// own slots until the flag of this launch shows up in all of them: one NVLink store latency instead of the two
+// signal-pad round trips of the one-shot kernel (13.4 -> ~6 us at np=8).  The flag is the per-block epoch counter, so
+// stale slots never match; slots alternate between two halves by flag parity, and a rank can only reach the launch
+// that reuses a half after every peer has sent (hence finished reading) the launch in between.  Fixed summation order.
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+allreduce_ll_kernel(CollCtx c, PeerPtrs ll, const char* ll_mine, uint4* data_mine, long long nvec, int op, float pre, float post) {
+  EpochScope ep(c);
+  const uint32_t flag = ep.base + 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < nvec) {
+    const int world = c.world;
+    const size_t half = (size_t)(flag & 1u) * kMaxPeers * kLLVecs;
+    uint4* data = data_mine + idx;
+    const uint4 mine = *data;
+    const unsigned long long f = (unsigned long long)flag << 32;
+    const unsigned long long w0 = f | mine.x, w1 = f | mine.y, w2 = f | mine.z, w3 = f | mine.w;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < world && p != c.rank) {
+        char* dst = static_cast<char*>(ll.p[p]) + (half + (size_t)c.rank * kLLVecs + idx) * kLLSlotBytes;
+        st_peer_v2_u64(dst, w0, w1);
+        st_peer_v2_u64(dst + 16, w2, w3);
+      }
+    uint4 v[kMaxPeers];
+    const unsigned long long t0 = globaltimer_ns();
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p >= world) continue;
+      if (p == c.rank) { v[p] = mine; continue; }
+      const char* src = ll_mine + (half + (size_t)p * kLLVecs + idx) * kLLSlotBytes;
+      unsigned long long a, b, d, e;
+      unsigned spins = 0;
+      for (;;) {
+        ld_peer_v2_u64(src, a, b);
+        ld_peer_v2_u64(src + 16, d, e);
+        if ((uint32_t)(a >> 32) == flag && (uint32_t)(b >> 32) == flag && (uint32_t)(d >> 32) == flag && (uint32_t)(e >> 32) == flag) break;
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > c.timeout_ns) {
+          *reinterpret_cast<volatile uint32_t*>(c.err) = 0x80000000u | ((uint32_t)p << 8) | (uint32_t)c.rank;
+          break;
+        }
+      }
+      v[p] = make_uint4((uint32_t)a, (uint32_t)b, (uint32_t)d, (uint32_t)e);
+    }
+    *data = reduce_vectors<T>(v, world, op, pre, post);
+  }
+  ep.commit(c, 1);
+}
+
+// =====================================================================================================
 // K2  two-shot allreduce over P2P, in place: rank r reduces slice r from all peers and pushes the
 // result straight into every peer's buffer (reduce-scatter and all-gather in one pass).
 // =====================================================================================================
@@ -536,8 +589,11 @@ static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int 
   const long long nvec = ceil_div_ll(numel * (long long)sizeof(T), 16);
   const long long bytes = nvec * 16;
   constexpr bool mc_type = std::is_same<T, float>::value || std::is_same<T, __nv_bfloat16>::value || std::is_same<T, __half>::value;
+  const bool ll_ok = c->world > 1 && c->ll_buf >= 0 && nvec <= kLLVecs;
+  if (algo == 4 && !ll_ok) algo = 0;
   if (algo == 0) {
     if (c->world == 1) algo = 1;
+    else if (ll_ok) algo = 4;
     else if (bytes <= (long long)c->oneshot_max_bytes && nvec <= (long long)c->max_blocks * kThreads * kOneShotR) algo = 1;
     // in-switch reduction halves the bytes a rank receives only when there are >= 3 peers to fold: at 2 ranks the
     // P2P two-shot moves the same bytes and measures 1.6x faster (417 vs 696 us at 256 MB, sweep of round 2)
@@ -551,7 +607,15 @@ static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int 
     c->last_error = "multimem allreduce needs a multicast-bound buffer, a float type and op=sum";
     return -1;
   }
-  if (algo == 1) {
+  if (algo == 4) {
+    PeerPtrs ll;
+    const int channel = (int)((ctx.epoch - c->epoch) / kMaxBlocks);
+    for (int p = 0; p < kMaxPeers; ++p)
+      ll.p[p] = p < c->world ? static_cast<char*>(c->bufs[c->ll_buf].ptrs[p]) + (size_t)channel * kLLChannelBytes : nullptr;
+    const int threads = nvec < kThreads ? (int)((nvec + 31) / 32 * 32) : kThreads;
+    allreduce_ll_kernel<T><<<(int)ceil_div_ll(nvec, threads), threads, 0, s>>>(ctx, ll, static_cast<const char*>(ll.p[c->rank]),
+                                                                              static_cast<uint4*>(ctx.data.p[c->rank]), nvec, op, pre, post);
+  } else if (algo == 1) {
     int blocks = (int)ceil_div_ll(nvec, (long long)kThreads * kOneShotR);
     if (blocks < 1) blocks = 1;
     allreduce_oneshot_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, nvec, op, pre, post);
@@ -575,7 +639,7 @@ using namespace sdlc;
 extern "C" {
 
 // In-place allreduce of `numel` elements at byte `offset` of symmetric buffer `buf`.
-// algo: 0 auto, 1 one-shot, 2 two-shot P2P, 3 two-shot NVLS.  Returns the algorithm used or -1.
+// algo: 0 auto, 1 one-shot, 2 two-shot P2P, 3 two-shot NVLS, 4 LL (flag-in-data, <= 64 KB).  Returns the algorithm used or -1.
 int sdlc_allreduce(void* h, int channel, int buf, long long offset, long long numel, int dtype, int op,
                    float pre, float post, int algo, unsigned long long stream) {
   Comm* c = static_cast<Comm*>(h);

@@ -393,6 +393,18 @@ int sdlc_comm_set_pads(void* h, int id) {
 }
 size_t sdlc_pad_bytes() { return sizeof(uint32_t) * kChannels * kPadWordsPerChannel; }
 
+// receive area of the LL (flag-in-data) allreduce: zero-filled symmetric buffer of sdlc_ll_bytes(); id < 0 disables
+int sdlc_comm_set_ll(void* h, int id) {
+  Comm* c = static_cast<Comm*>(h);
+  if (id >= 0 && c->bufs[id].bytes < kLLChannelBytes * kChannels) {
+    c->last_error = "LL buffer too small";
+    return -1;
+  }
+  c->ll_buf = id;
+  return 0;
+}
+size_t sdlc_ll_bytes() { return kLLChannelBytes * kChannels; }
+
 int sdlc_comm_set_staging(void* h, int channel, int id) {
   static_cast<Comm*>(h)->staging_buf[channel] = id;
   return 0;

@@ -34,6 +34,7 @@ struct Comm {
   int rank = 0, world = 1, device = 0;
   std::vector<SymmBuffer> bufs;
   int pad_buf = -1;                       // symmetric signal-pad buffer
+  int ll_buf = -1;                        // symmetric receive area of the flag-in-data small-message path (or -1)
   int staging_buf[kChannels] = {-1, -1, -1, -1};
   uint32_t* epoch = nullptr;              // device: kChannels * kMaxBlocks counters
   uint32_t* err_host = nullptr;           // pinned + mapped

@@ -19,6 +19,10 @@ constexpr int kMaxBlocks = 128;     // CTAs of one collective launch
 constexpr int kChannels = 4;        // independent flag sets: 0 engine, 1 optimizer, 2 gbdt, 3 spare
 constexpr int kPadWordsPerChannel = kMaxBlocks * kMaxPeers;
 constexpr int kThreads = 512;
+constexpr int kLLVecs = 4096;       // 16-byte vectors per message on the flag-in-data (LL) path: 64 KB
+// LL receive area per channel: [parity 2][source rank kMaxPeers][kLLVecs] slots of 32 bytes (4 x {data32, flag32})
+constexpr size_t kLLSlotBytes = 32;
+constexpr size_t kLLChannelBytes = 2ull * kMaxPeers * kLLVecs * kLLSlotBytes;
 
 // dtype / op codes: keep in sync with csrc/core/common.h
 enum DType : uint32_t { kU8 = 0, kI8 = 1, kI32 = 2, kI64 = 3, kF16 = 4, kBF16 = 5, kF32 = 6, kF64 = 7, kBool = 8, kF8 = 9 };
@@ -71,6 +75,13 @@ __device__ __forceinline__ uint2 ld_peer_v2(const void* p) {
 __device__ __forceinline__ void st_peer_v2(void* p, const uint2& v) {
   asm volatile("st.relaxed.sys.global.L1::no_allocate.v2.u32 [%0], {%1,%2};"
                ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+// two 64-bit words; every 64-bit element is single-copy atomic, so a {data, flag} pair can never be seen half-written
+__device__ __forceinline__ void st_peer_v2_u64(void* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.sys.global.L1::no_allocate.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_peer_v2_u64(const void* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.sys.global.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_peer_u32(const void* p) {
   uint32_t v;

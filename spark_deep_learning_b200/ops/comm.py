@@ -24,7 +24,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = None
 
 WIRE = {None: 0, "bf16": 1, "fp16": 2, "fp8": 3}
-ALGO = {"auto": 0, "oneshot": 1, "twoshot": 2, "multimem": 3}
+ALGO = {"auto": 0, "oneshot": 1, "twoshot": 2, "multimem": 3, "ll": 4}
 _TORCH_DTYPE = {
     torch.uint8: _core.U8, torch.int8: _core.I8, torch.int32: _core.I32, torch.int64: _core.I64,
     torch.float16: _core.F16, torch.bfloat16: _core.BF16, torch.float32: _core.F32,
@@ -83,6 +83,8 @@ def load():
         "sdlc_check_error": (ctypes.c_uint, [vp]),
         "sdlc_clear_error": (None, [vp]),
         "sdlc_launch_count": (u64, [vp]),
+        "sdlc_comm_set_ll": (i32, [vp, i32]),
+        "sdlc_ll_bytes": (ctypes.c_size_t, []),
         "sdlc_max_peers": (i32, []),
         "sdlc_allreduce": (i32, [vp, i32, i32, i64, i64, i32, i32, f32, f32, i32, u64]),
         "sdlc_wire_bytes": (i64, [i64, i32]),
@@ -225,6 +227,11 @@ class SymmComm(object):
         if self._lib.sdlc_comm_set_pads(self._h, pads.id):
             raise CommError(self._err())
         self.pads = pads
+        if self.world > 1 and os.environ.get("SPARKDL_LL_ALLREDUCE", "1") != "0":
+            # receive slots of the barrier-free small-message allreduce (<= 64 KB), zero-filled by the allocator
+            self._ll = self.alloc_symmetric(self._lib.sdlc_ll_bytes(), multicast=False)
+            if self._lib.sdlc_comm_set_ll(self._h, self._ll.id):
+                raise CommError(self._err())
         staging_bytes = max(int(cfg.fusion_threshold) + (4 << 20), 16 << 20)
         self.staging = self.alloc_symmetric(staging_bytes)
         self._lib.sdlc_comm_set_staging(self._h, 0, self.staging.id)
@@ -621,6 +628,10 @@ class VirtualGroup(object):
         self.pads = self.alloc(lib.sdlc_pad_bytes())
         for c, p in zip(self.comms, self.pads):
             lib.sdlc_comm_set_pads(c._h, p.id)
+        if world > 1:
+            self.ll = self.alloc(lib.sdlc_ll_bytes())
+            for c, b in zip(self.comms, self.ll):
+                lib.sdlc_comm_set_ll(c._h, b.id)
         self.streams = [torch.cuda.Stream(device=device) for _ in range(world)]
 
     def alloc(self, nbytes):

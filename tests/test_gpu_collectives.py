@@ -52,11 +52,11 @@ def _launch_all(vg, fn):
 
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 4])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_allreduce_sum(lib, world, algo, dtype):
     vg = _group(world)
-    n = 4096 * 3 + 8 if algo == 2 else 4096 + 8
+    n = 4096 * 3 + 8 if algo == 2 else 4096 + 8          # algo 4 = LL (flag-in-data); world 1 falls back to one-shot
     bufs = vg.alloc(n * 4)
     srcs = _fill(bufs, dtype, n)
     ref = sum(s.float() for s in srcs) * 0.5

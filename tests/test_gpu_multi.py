@@ -34,8 +34,8 @@ def _symmetric_allreduce_main():
     max_bytes = 24 << 20
     buf = comm.alloc_symmetric(max_bytes)
     info = {"transport": comm.transport, "multicast": bool(comm.multicast and buf.multicast), "bad": [], "ran": {}}
-    algos = ["oneshot", "twoshot"] + (["multimem"] if info["multicast"] else [])
-    sizes = [1, 7, 8, 1000, 4099, 65537, (1 << 20) + 3, (4 << 20) + 5]
+    algos = ["ll", "oneshot", "twoshot"] + (["multimem"] if info["multicast"] else [])
+    sizes = [1, 7, 8, 1000, 4099, 16384, 65537, (1 << 20) + 3, (4 << 20) + 5]
     for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 2e-2), (torch.float16, 2e-3)):
         esz = torch.empty(0, dtype=dt).element_size()
         for numel in sizes:
@@ -43,6 +43,8 @@ def _symmetric_allreduce_main():
             exp = sum(((idx * 7 + q * 3) % 11 + 1).float() * 0.25 for q in range(n)) / n
             for algo in algos:
                 if algo == "oneshot" and numel * esz > (8 << 20):
+                    continue
+                if algo == "ll" and numel * esz > (64 << 10):      # flag-in-data path: messages of at most 64 KB
                     continue
                 view = buf.tensor(dt, numel)
                 view.copy_((((idx * 7 + r * 3) % 11 + 1).float() * 0.25).to(dt))
@@ -60,6 +62,19 @@ def _symmetric_allreduce_main():
                 if not (ok and same):
                     info["bad"].append((str(dt), numel, algo, ok, same))
                 hvd.barrier()
+    # 200 back-to-back LL launches of alternating sizes without any barrier in between (slot halves alternate by parity)
+    view = buf.tensor(torch.float32, 16384)
+    view.fill_(1.0)
+    torch.cuda.synchronize()
+    hvd.barrier()
+    for i in range(200):
+        ev = comm.allreduce_symmetric(buf, 16384 if i % 3 else 100, torch.float32, op=core.OP_SUM, post=1.0 / n, channel=2, algo="ll")
+    comm.current_stream_wait(ev, release=True)
+    torch.cuda.synchronize()
+    comm.check_error()
+    if not bool((view == 1.0).all().item()):
+        info["bad"].append(("float32", 16384, "ll-repeat", False, False))
+    info["ran"]["ll-repeat"] = 200
     # op = min / max and int dtypes go through the P2P kernels
     for op_name, op, fn in (("min", core.OP_MIN, min), ("max", core.OP_MAX, max)):
         view = buf.tensor(torch.float32, 5003)
@@ -94,6 +109,7 @@ def test_symmetric_allreduce_all_algorithms_dtypes_and_tails():
     info = HorovodRunner(np=_np()).run(_symmetric_allreduce_main)
     assert not info["bad"], info
     assert info["ran"].get("oneshot", 0) > 0 and info["ran"].get("twoshot", 0) > 0
+    assert info["ran"].get("ll", 0) >= 15 and info["ran"].get("ll-repeat") == 200, info
     if info["transport"] == "vmm":
         assert info["multicast"] and info["ran"].get("multimem", 0) >= 20, info   # NVLS path really ran
     assert info["event_pool"] < 64      # events are recycled, not leaked
