@@ -93,7 +93,7 @@ def sweep(max_mb=1024, iters=20, warmup=5, dtypes=("float32", "bfloat16"), with_
                 row[name + "_us"] = round(ms * 1e3, 2)
                 row[name + "_busbw"] = round(2 * (world - 1) / world * nb / (ms * 1e-3) / 1e9, 2) if world > 1 else None
             if nb >= (4 << 20):    # how many CTAs does it take to saturate NVLink?  (default: SPARKDL_COMM_CTAS = 32)
-                for ctas in ((16, 48, 64, 96, 128) if nb <= (64 << 20) else (64, 128)):
+                for ctas in ((16, 64, 128) if nb <= (64 << 20) else (64, 128)):
                     lib.sdlc_comm_set_max_blocks(comm._h, ctas)
                     for name, algo in algos[1:]:
                         def fnb(algo=algo, n=n):

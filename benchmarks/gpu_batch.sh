@@ -27,9 +27,9 @@ for stage in "$@"; do
                (timeout 300 python benchmarks/bert_probe.py 2>&1 | tail -30) > gpurun_out/bert_probe.txt
                tail -12 gpurun_out/resnet_probe.txt gpurun_out/bert_probe.txt ;;
     xgbprof)   (XGB_PROFILE=gpurun_out/xgb_profile.txt XGB_BENCH_SKLEARN=0 timeout 400 python benchmarks/xgboost_bench.py --np 1 2>&1 | tail -3) > gpurun_out/xgb_prof.log; cat gpurun_out/xgb_prof.log; cut -c1-200 gpurun_out/xgb_profile.txt | head -80 ;;
-    xgb)       NPX=${XGB_NP:-1}; (timeout 300 python -m pytest tests/test_gpu_xgboost.py -q -m gpu 2>&1 | tail -5) > gpurun_out/pytest_xgb.txt; cat gpurun_out/pytest_xgb.txt
+    xgb)       NPX=${XGB_NP:-1}; if [ -z "$XGB_SKIP_GA" ]; then (timeout 300 python -m pytest tests/test_gpu_xgboost.py -q -m gpu 2>&1 | tail -5) > gpurun_out/pytest_xgb.txt; cat gpurun_out/pytest_xgb.txt; fi
                (timeout 400 python benchmarks/xgboost_bench.py --np $NPX --out gpurun_out/xgboost_bench_np$NPX.json 2>&1 | tail -4) > gpurun_out/xgb_np$NPX.txt; cat gpurun_out/xgb_np$NPX.txt
-               (SPARKDL_GBDT_SMEM_HIST=0 timeout 400 python benchmarks/xgboost_bench.py --np $NPX --out gpurun_out/xgboost_bench_np${NPX}_globalatomics.json 2>&1 | tail -2) > gpurun_out/xgb_np${NPX}_ga.txt; cat gpurun_out/xgb_np${NPX}_ga.txt ;;
+               if [ -z "$XGB_SKIP_GA" ]; then (SPARKDL_GBDT_SMEM_HIST=0 timeout 400 python benchmarks/xgboost_bench.py --np $NPX --out gpurun_out/xgboost_bench_np${NPX}_globalatomics.json 2>&1 | tail -2) > gpurun_out/xgb_np${NPX}_ga.txt; cat gpurun_out/xgb_np${NPX}_ga.txt; fi ;;
     profbert)  (timeout 300 python benchmarks/step_profile.py bert 2>&1 | tail -5) > gpurun_out/step_profile_bert.log; cat gpurun_out/step_profile_bert.log ;;
     profresnet) (timeout 300 python benchmarks/step_profile.py resnet 2>&1 | tail -5) > gpurun_out/step_profile_resnet.log; cat gpurun_out/step_profile_resnet.log ;;
     sdpaprobe) (timeout 120 python benchmarks/sdpa_probe.py 2>&1 | tail -20) > gpurun_out/sdpa_probe.txt; cat gpurun_out/sdpa_probe.txt ;;
@@ -63,7 +63,7 @@ for stage in "$@"; do
     racedetail) (timeout 500 compute-sanitizer --print-limit 30 --tool racecheck python -m pytest tests/test_gpu_layernorm.py tests/test_gpu_xgboost.py -q -x -k "not distributed" 2>&1 | grep -E "=========|passed|failed" | grep -v "=========     at \|=========     in " | cut -c1-300 | tail -80) > gpurun_out/sanitizer_racecheck_ln_xent_gbdt.txt; cat gpurun_out/sanitizer_racecheck_ln_xent_gbdt.txt ;;
     nvlink)    NPX=${NVL_NP:-2}; (timeout 300 python benchmarks/nvlink_counters.py --np $NPX --out gpurun_out/nvlink_np$NPX.json 2>&1 | tail -12) > gpurun_out/nvlink_np$NPX.txt; cat gpurun_out/nvlink_np$NPX.txt ;;
     benchN)    N=${BENCH_NP:-2}; PORT=29611
-               for m in resnet50 bert-large; do for impl in ours reference; do
+               for m in resnet50 bert-large; do for impl in ${BENCH_IMPLS:-ours reference}; do
                  PORT=$((PORT+1)); tag=$(echo $m | cut -c1-4)${N}_$impl
                  (timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $N --steps 20 --warmup 5 --model $m --impl $impl 2> gpurun_out/$tag.err | tail -1) > gpurun_out/$tag.json; cut -c1-420 gpurun_out/$tag.json
                done; done ;;

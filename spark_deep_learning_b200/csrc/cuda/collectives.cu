@@ -589,7 +589,7 @@ static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int 
   const long long nvec = ceil_div_ll(numel * (long long)sizeof(T), 16);
   const long long bytes = nvec * 16;
   constexpr bool mc_type = std::is_same<T, float>::value || std::is_same<T, __nv_bfloat16>::value || std::is_same<T, __half>::value;
-  const bool ll_ok = c->world > 1 && c->ll_buf >= 0 && nvec <= kLLVecs;
+  const bool ll_ok = c->world > 1 && c->ll_buf >= 0 && nvec > 0 && nvec <= kLLVecs;
   if (algo == 4 && !ll_ok) algo = 0;
   if (algo == 0) {
     if (c->world == 1) algo = 1;
@@ -597,7 +597,7 @@ static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int 
     else if (bytes <= (long long)c->oneshot_max_bytes && nvec <= (long long)c->max_blocks * kThreads * kOneShotR) algo = 1;
     // in-switch reduction halves the bytes a rank receives only when there are >= 3 peers to fold: at 2 ranks the
     // P2P two-shot moves the same bytes and measures 1.6x faster (417 vs 696 us at 256 MB, sweep of round 2)
-    else if (ctx.mc != nullptr && mc_type && op == kSum && c->world > 2) algo = 3;
+    else if (ctx.mc != nullptr && mc_type && op == kSum && c->world >= c->nvls_min_world) algo = 3;
     else algo = 2;
   }
   if (algo == 1) {

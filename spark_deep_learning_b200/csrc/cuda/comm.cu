@@ -1,3 +1,5 @@
+#include <cstdlib>
+
 #include "comm.h"
 
 #include <unistd.h>
@@ -136,6 +138,7 @@ void* sdlc_comm_create(int rank, int world, int device, double timeout_ms, int m
   c->max_blocks = max_blocks < 1 ? 1 : (max_blocks > kMaxBlocks ? kMaxBlocks : max_blocks);
   c->oneshot_max_bytes = (size_t)oneshot_max_bytes;
   c->use_mc = use_mc != 0;
+  if (const char* e = getenv("SPARKDL_NVLS_MIN_WORLD")) c->nvls_min_world = atoi(e) < 2 ? 2 : atoi(e);
   if (cudaSetDevice(device) != cudaSuccess) {
     delete c;
     return nullptr;

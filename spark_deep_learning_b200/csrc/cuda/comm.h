@@ -44,6 +44,9 @@ struct Comm {
   int max_blocks = 32;
   size_t oneshot_max_bytes = 512 << 10;
   bool use_mc = true;
+  // In-switch reduction pays when there are >= 3 copies to fold: at 2 ranks NVLS moves 1.5 S per direction through
+  // the links, the P2P kernels 1.0 S (NVML link counters, benchmarks/nvlink_counters.py).  SPARKDL_NVLS_MIN_WORLD.
+  int nvls_min_world = 3;
   std::mutex mu;
   // Owned events: an event handed out by acquire_event() is never re-recorded until every holder has
   // released it (a round-robin ring could wrap onto an event that a pending cudaStreamWaitEvent still needs).

@@ -69,6 +69,8 @@ def _symmetric_allreduce_main():
     hvd.barrier()
     for i in range(200):
         ev = comm.allreduce_symmetric(buf, 16384 if i % 3 else 100, torch.float32, op=core.OP_SUM, post=1.0 / n, channel=2, algo="ll")
+        if i < 199:
+            comm.release_event(ev)
     comm.current_stream_wait(ev, release=True)
     torch.cuda.synchronize()
     comm.check_error()
@@ -214,8 +216,11 @@ def _fused_bf16_main(opt_name):
     return diff / scale, bool((sig == sig[0]).all().item()), sym, hvd.comm_backend().multicast
 
 
+@pytest.mark.parametrize("nvls_min_world", ["2", "3"])
 @pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
-def test_fused_step_bf16_master_weights_multicast(opt_name):
+def test_fused_step_bf16_master_weights_multicast(opt_name, nvls_min_world, monkeypatch):
+    # "2": the multimem (NVLS) branches of fused_step_kernel even on a 2-GPU box; "3" (default): peer-to-peer at 2 ranks
+    monkeypatch.setenv("SPARKDL_NVLS_MIN_WORLD", nvls_min_world)
     rel, same, sym, _ = HorovodRunner(np=_np()).run(_fused_bf16_main, opt_name=opt_name)
     assert same and sym
     # bf16 forward/backward vs an fp32 replica of the whole batch; Adam turns bf16 noise on tiny gradients into
