@@ -34,7 +34,7 @@ def sweep(max_mb=256, iters=10):
 
     def timed(fn, k):
         for _ in range(2):
-            fn()
+            fn(k)            # same number of operations in flight as the timed call: the allocator is warm
         torch.cuda.synchronize()
         hvd.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

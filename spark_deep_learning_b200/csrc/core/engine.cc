@@ -759,6 +759,18 @@ void Engine::execute(const Response& r) {
       if (!e) { err = "internal: allgather response without a local entry"; break; }
       if (r.device >= 0) {
         if (!gpu_fn_) { complete(e, "CUDA tensor submitted but no GPU executor is registered"); return; }
+        // root == 1: the callers sized their output buffers for equal shards (world x own rows) without asking first.
+        // The response carries every rank's rows, so all ranks take the same decision here: run when the shards are
+        // equal, otherwise complete without touching the buffers - the caller sees out_dim0 != its guess and
+        // re-submits with exact sizes (root == 0).  One negotiation instead of two in the common case.
+        int64_t rows = 0;
+        bool equal = true;
+        for (int p = 0; p < world; ++p) {
+          rows += r.dim0[p];
+          equal = equal && r.dim0[p] == r.dim0[0];
+        }
+        if (auto st0 = state(e->handle)) st0->out_dim0 = rows;
+        if (r.root == 1 && !equal) { complete(e, ""); return; }
         GpuWork w;
         memset(&w, 0, sizeof(w));
         w.type = r.type; w.dtype = r.dtype; w.device = r.device; w.n = 1;

@@ -563,10 +563,10 @@ __global__ void __launch_bounds__(256) scale_kernel(T* p, long long n, float s) 
 // keeps loads to 7 peers in flight; with fewer peers a CTA has proportionally fewer bytes in flight over NVLink
 // (round 1: 357-400 GB/s at np=2 with 32 CTAs vs 508 GB/s for NCCL), so the cap scales with 8 / world.  The result
 // depends on rank-independent values only (the in-kernel barrier pairs CTA b of every rank).
-static int pick_blocks(const Comm* c, long long work_items, int per_block) {
+static int pick_blocks(const Comm* c, long long work_items, int per_block, int base_cap = 0) {
   long long b = ceil_div_ll(work_items, per_block);
   if (b < 1) b = 1;
-  long long cap = c->max_blocks;
+  long long cap = base_cap > 0 ? base_cap : c->max_blocks;
   if (c->world > 1 && c->world < 8) cap = cap * (8 / c->world);
   if (cap > kMaxBlocks) cap = kMaxBlocks;
   if (b > cap) b = cap;
@@ -589,11 +589,13 @@ static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int 
   const long long nvec = ceil_div_ll(numel * (long long)sizeof(T), 16);
   const long long bytes = nvec * 16;
   constexpr bool mc_type = std::is_same<T, float>::value || std::is_same<T, __nv_bfloat16>::value || std::is_same<T, __half>::value;
-  const bool ll_ok = c->world > 1 && c->ll_buf >= 0 && nvec > 0 && nvec <= kLLVecs;
+  // LL pays while (world - 1) x message stays small: 64 KB at 2 ranks, ~18 KB at 8 (13.6 us NVLS vs 14.3 us LL at 64 KB, np=8)
+  const bool ll_ok = c->world > 1 && c->ll_buf >= 0 && nvec > 0 && nvec <= kLLVecs;      // fits the receive slots
+  const bool ll_pays = ll_ok && nvec * (c->world - 1) <= 2 * kLLVecs;
   if (algo == 4 && !ll_ok) algo = 0;
   if (algo == 0) {
     if (c->world == 1) algo = 1;
-    else if (ll_ok) algo = 4;
+    else if (ll_pays) algo = 4;
     else if (bytes <= (long long)c->oneshot_max_bytes && nvec <= (long long)c->max_blocks * kThreads * kOneShotR) algo = 1;
     // in-switch reduction halves the bytes a rank receives only when there are >= 3 peers to fold: at 2 ranks the
     // P2P two-shot moves the same bytes and measures 1.6x faster (417 vs 696 us at 256 MB, sweep of round 2)
@@ -624,7 +626,10 @@ static int launch_allreduce_t(Comm* c, const CollCtx& ctx, long long numel, int 
     allreduce_twoshot_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, nvec, op, pre, post);
   } else {
     if constexpr (mc_type) {
-      const int blocks = pick_blocks(c, ceil_div_ll(nvec, c->world), kThreads * 8);
+      // up to 64 MB fewer CTAs are faster through the switch (np=8 sweep of round 2: 649 / 587 / 533 GB/s bus bandwidth
+      // at 32 MB with 16 / 32 / 64 CTAs, 732 / 694 / 646 at 64 MB); from 128 MB on the configured count wins
+      const int cap = (bytes <= (64ll << 20) && c->max_blocks > 16) ? 16 : 0;
+      const int blocks = pick_blocks(c, ceil_div_ll(nvec, c->world), kThreads * 8, cap);
       allreduce_multimem_kernel<T><<<blocks, kThreads, 0, s>>>(ctx, nvec, pre * post);
     }
   }

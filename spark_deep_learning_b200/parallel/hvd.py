@@ -620,10 +620,30 @@ def allgather_async(tensor, name=None, process_set=None):  # pylint: disable=unu
     if src.dim() == 0:
         src = src.reshape(1)
     if src.is_cuda:
-        sizes = _host_allgather_ints([src.shape[0]], name + ".dim0").reshape(-1).tolist()
-        out = torch.empty((sum(sizes),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
-        h = _enqueue(_core.ALLGATHER, name, src, out)
-        return _Handle([h], out, (src, out), None, True)
+        # optimistic: size the output for equal shards and let the negotiation response (which carries every rank's
+        # rows) confirm it - one round trip and no host sync.  Unequal shards: the engine leaves the buffers alone on
+        # every rank and the exact-size path below runs at synchronize() time.
+        n = size()
+        out = torch.empty((n * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        h = _enqueue(_core.ALLGATHER, name, src, out, root=1)
+
+        def exact(hd, _src=src, _h=h, _out=out, _name=name):
+            if _S.engine.out_dim0(_h) == _out.shape[0]:
+                return _out
+            sizes = _host_allgather_ints([_src.shape[0]], _name + ".dim0").reshape(-1).tolist()
+            full = torch.empty((sum(sizes),) + tuple(_src.shape[1:]), dtype=_src.dtype, device=_src.device)
+            h2 = _enqueue(_core.ALLGATHER, _name + ".exact", _src, full)
+            try:
+                _S.engine.wait(h2)
+                ev = _S.engine.done_event(h2)
+                if ev:
+                    _S.comm.current_stream_wait(ev, release=True)
+            except _core.EngineError as e:
+                raise HorovodInternalError(str(e))
+            finally:
+                _S.engine.release(h2)
+            return full
+        return _Handle([h], out, (src, out), exact, True)
     h = _enqueue(_core.ALLGATHER, name, src, None)
 
     def post(hd, _src=src, _h=h):
