@@ -67,6 +67,8 @@ for stage in "$@"; do
                  PORT=$((PORT+1)); tag=$(echo $m | cut -c1-4)${N}_$impl
                  (timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $N --steps 20 --warmup 5 --model $m --impl $impl 2> gpurun_out/$tag.err | tail -1) > gpurun_out/$tag.json; cut -c1-420 gpurun_out/$tag.json
                done; done ;;
+    forklab)   for cfg in "0 0" "1 0" "1 1" "1 2" "1 3"; do set -- $cfg; echo "fork=$1 variant=$2"; (SPARKDL_BN_FORK=$1 SPARKDL_BN_FORK_VARIANT=$2 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 2>/dev/null | tail -1 | grep -o '"ms_per_step": [0-9.]*'); done > gpurun_out/fork_lab.txt 2>&1; cat gpurun_out/fork_lab.txt ;;
+    cudnnlab)  for lim in 10 0; do echo "cudnn benchmark_limit=$lim"; (SPARKDL_CUDNN_BENCH_LIMIT=$lim timeout 400 python bench.py --gpus 1 --steps 20 --warmup 5 2>/dev/null | tail -1 | grep -o '"ms_per_step": [0-9.]*'); done > gpurun_out/cudnn_lab.txt 2>&1; cat gpurun_out/cudnn_lab.txt ;;
     sanitize)  bash benchmarks/sanitize.sh ;;
     *)         echo "unknown stage $stage" ;;
   esac

@@ -22,6 +22,8 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
     dev = torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(1234)
     torch.backends.cudnn.benchmark = True
+    if os.environ.get("SPARKDL_CUDNN_BENCH_LIMIT"):
+        torch.backends.cudnn.benchmark_limit = int(os.environ["SPARKDL_CUDNN_BENCH_LIMIT"])   # 0 = try every algorithm
     comm = hvd.comm_backend()
 
     bf16_weights = bool(fused_optimizer and fused_model)     # fp32 masters live in the fused optimizer's state

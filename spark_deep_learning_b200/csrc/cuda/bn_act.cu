@@ -123,12 +123,14 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long 
 }
 
 // ---------------- finalize: mean / rstd / fused scale+shift, running statistics ----------------------
-// Block = 32 channels x 32 row groups: the per-block partials are summed by 32 threads per channel
-// (coalesced 128-byte rows), then combined through shared memory in a fixed order (deterministic).
-constexpr int kFinX = 32, kFinY = 32;   // 1024 threads: the partial-row loop is latency bound, so go wide
+// Block = 8 channels x 128 row groups (1024 threads), grid = C / 8.  The loop over the per-block partial rows is pure
+// L2 latency, so it is made as short as possible: with 592 partial rows a thread issues at most 5 independent 32-byte
+// row reads in one go.  The 128 row groups are then folded in a fixed order (warp shuffles over the 4 groups of a warp,
+// shared memory across the 32 warps, shuffles again in warp 0): deterministic, and threads (x, y = 0) own the result.
+constexpr int kFinX = 8, kFinY = 128;
 
 __device__ __forceinline__ void sum_partials(const float* __restrict__ partial, int nblocks, int C, int c, float& s, float& q) {
-  __shared__ float sh[2][kFinY][kFinX];
+  __shared__ float sh[2][32][kFinX];
   float a = 0.f, b = 0.f;
   if (c < C) {
     int r = threadIdx.y;
@@ -142,17 +144,31 @@ __device__ __forceinline__ void sum_partials(const float* __restrict__ partial, 
 #pragma unroll
       for (int u = 0; u < 4; ++u) { a += t0[u]; b += t1[u]; }
     }
-    for (; r < nblocks; r += kFinY) {
-      a += partial[(long long)r * 2 * C + c];
-      b += partial[(long long)r * 2 * C + C + c];
-    }
+    float t0[3] = {0.f, 0.f, 0.f}, t1[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (r + u * kFinY < nblocks) {
+        t0[u] = partial[(long long)(r + u * kFinY) * 2 * C + c];
+        t1[u] = partial[(long long)(r + u * kFinY) * 2 * C + C + c];
+      }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) { a += t0[u]; b += t1[u]; }
   }
-  sh[0][threadIdx.y][threadIdx.x] = a;
-  sh[1][threadIdx.y][threadIdx.x] = b;
+  // lane = (y & 3) * 8 + x: fold the 4 row groups of this warp
+  a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+  a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+  const int tid = threadIdx.y * kFinX + threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (lane < kFinX) { sh[0][warp][lane] = a; sh[1][warp][lane] = b; }
   __syncthreads();
   s = 0.f; q = 0.f;
+  if (warp == 0) {
+    // lane = part * 8 + x: part p adds warps 8p .. 8p+7 in order, then the 4 parts are folded
+    const int x = lane & 7, part = lane >> 3;
 #pragma unroll
-  for (int y = 0; y < kFinY; ++y) { s += sh[0][y][threadIdx.x]; q += sh[1][y][threadIdx.x]; }
+    for (int w = 0; w < 8; ++w) { s += sh[0][part * 8 + w][x]; q += sh[1][part * 8 + w][x]; }
+    s += __shfl_xor_sync(0xffffffffu, s, 8);  q += __shfl_xor_sync(0xffffffffu, q, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16); q += __shfl_xor_sync(0xffffffffu, q, 16);
+  }
 }
 
 __global__ void __launch_bounds__(kFinX * kFinY)
@@ -238,10 +254,12 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restric
 // ---------------- backward pass 1: partial sum(dz), sum(dz * x) -------------------------------------------
 // (sum(dz * xhat) = rstd * (sum(dz*x) - mean * sum(dz)) is formed in the finalize kernel: the streaming
 // loop keeps no per-channel constants in registers, which buys occupancy.)
-template <typename T>
+// HAS2: the incoming gradient is the sum of two tensors (the block output feeds both the next block's first convolution
+// and its identity / downsample branch); adding them here saves the separate add pass autograd would run.
+template <typename T, bool HAS2>
 __global__ void __launch_bounds__(kThreads)
-bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask,
-                     float* __restrict__ partial, long long nvec, int C, int relu) {
+bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ x,
+                     const uint8_t* __restrict__ mask, float* __restrict__ partial, long long nvec, int C, int relu) {
   constexpr int N = V<T>::N;
   const int CV = C / N;
   extern __shared__ float smem[];
@@ -262,6 +280,16 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const ui
       V<T>::load(dy + v1 * N, d1);
       V<T>::load(x + v1 * N, f1);
       if (relu) m1 = mask[v1];
+    }
+    if (HAS2) {
+      float e0[N], e1[N];
+      V<T>::load(dy2 + v0 * N, e0);
+      if (h1) V<T>::load(dy2 + v1 * N, e1);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        d0[i] += e0[i];
+        if (h1) d1[i] += e1[i];
+      }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -293,15 +321,16 @@ __global__ void __launch_bounds__(kFinX * kFinY)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, float inv_m,
                        const float* __restrict__ weight, const float* __restrict__ mean, const float* __restrict__ rstd,
                        float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ c0,
-                       float* __restrict__ c1, float* __restrict__ c2) {
+                       float* __restrict__ c1, float* __restrict__ c2, int accumulate) {
   const int c = blockIdx.x * kFinX + threadIdx.x;
   float s, q;
   sum_partials(partial, nblocks, C, c, s, q);
   if (c >= C || threadIdx.y != 0) return;
   const float mu = mean[c], rs = rstd[c];
   const float dgamma = rs * (q - mu * s);      // sum(dz * xhat)
-  dbias[c] = s;
-  dweight[c] = dgamma;
+  // accumulate: dweight / dbias are views of a gradient bucket that other backward passes also add to
+  dbias[c] = accumulate ? dbias[c] + s : s;
+  dweight[c] = accumulate ? dweight[c] + dgamma : dgamma;
   // dx = a*(dz - s/M - xhat*dgamma/M)  with a = gamma*rstd, xhat = (x-mu)*rs   ==>   dx = A*dz + B*x + D
   const float a = (weight ? weight[c] : 1.f) * rs;
   const float k2 = dgamma * inv_m * rs;
@@ -328,9 +357,9 @@ template <> __device__ __forceinline__ void store_streaming<float>(float* p, con
 // Five streams (dy, x, mask in; dx, dz out): U vectors per thread are loaded before any math or store so that enough
 // bytes are in flight to cover HBM latency, and the outputs (each read exactly once, much later, by the next backward
 // kernel) are written with streaming stores so they do not evict the inputs of this pass from L2.
-template <typename T, int U, bool STREAM, int MINB>
+template <typename T, int U, bool STREAM, int MINB, bool HAS2 = false>
 __global__ void __launch_bounds__(kThreads, MINB)
-bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask,
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ x, const uint8_t* __restrict__ mask,
                     const float* __restrict__ c0, const float* __restrict__ c1, const float* __restrict__ c2,
                     T* __restrict__ dx, T* __restrict__ dz_out, long long nvec, int C, int relu) {
   constexpr int N = V<T>::N;
@@ -356,6 +385,18 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uin
         V<T>::load(dy + v * N, d[u]);
         V<T>::load(x + v * N, f[u]);
         if (relu) m[u] = mask[v];
+      }
+    }
+    if (HAS2) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long v = v0 + u * T_all;
+        if (v < nvec) {
+          float e[N];
+          V<T>::load(dy2 + v * N, e);
+#pragma unroll
+          for (int i = 0; i < N; ++i) d[u][i] += e[i];
+        }
       }
     }
 #pragma unroll
@@ -432,9 +473,9 @@ int sdlc_bn_fwd(const void* x, const void* res, void* y, void* mask, const float
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int sdlc_bn_bwd(const void* dy, const void* x, const void* mask, const float* weight, const float* mean, const float* rstd,
+int sdlc_bn_bwd(const void* dy, const void* dy2, const void* x, const void* mask, const float* weight, const float* mean, const float* rstd,
                 void* dx, void* dz, float* dweight, float* dbias, float* c0, float* c1, float* c2, float* partial,
-                long long m, int c, int relu, int dtype, unsigned long long stream) {
+                long long m, int c, int relu, int dtype, int accumulate, unsigned long long stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int n = dtype == 6 ? 4 : 8;
   if (c % n != 0 || (dtype != 5 && dtype != 6)) return -2;
@@ -443,19 +484,35 @@ int sdlc_bn_bwd(const void* dy, const void* x, const void* mask, const float* we
   const int grid = grid_for(nvec, cv);
   const size_t smem = cv < kThreads ? sizeof(float) * kThreads * 2 * n : 0;
   if (cv > kThreads) cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * 2 * c, s);
-  if (dtype == 5)
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
-                                                                    static_cast<const uint8_t*>(mask), partial, nvec, c, relu);
-  else
-    bn_bwd_reduce_kernel<float><<<grid, kThreads, smem, s>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
-                                                            static_cast<const uint8_t*>(mask), partial, nvec, c, relu);
-  bn_bwd_finalize_kernel<<<(c + kFinX - 1) / kFinX, dim3(kFinX, kFinY), 0, s>>>(partial, grid, c, 1.f / (float)m, weight, mean, rstd, dweight, dbias, c0, c1, c2);
+#define BWD_REDUCE(TT, H2)                                                                                                 \
+  bn_bwd_reduce_kernel<TT, H2><<<grid, kThreads, smem, s>>>(static_cast<const TT*>(dy), static_cast<const TT*>(dy2),       \
+                                                            static_cast<const TT*>(x), static_cast<const uint8_t*>(mask), \
+                                                            partial, nvec, c, relu)
+  if (dtype == 5) { if (dy2) BWD_REDUCE(__nv_bfloat16, true); else BWD_REDUCE(__nv_bfloat16, false); }
+  else { if (dy2) BWD_REDUCE(float, true); else BWD_REDUCE(float, false); }
+  bn_bwd_finalize_kernel<<<(c + kFinX - 1) / kFinX, dim3(kFinX, kFinY), 0, s>>>(partial, grid, c, 1.f / (float)m, weight, mean, rstd, dweight, dbias, c0, c1, c2, accumulate);
   static int variant = -1;
   if (variant < 0) { const char* e = getenv("SPARKDL_BN_BWD_VARIANT"); variant = e ? atoi(e) : 0; }
-#define BWD_APPLY(TT, UU, ST, MB)                                                                                          \
-  bn_bwd_apply_kernel<TT, UU, ST, MB><<<grid, kThreads, 0, s>>>(static_cast<const TT*>(dy), static_cast<const TT*>(x),      \
-                                                               static_cast<const uint8_t*>(mask), c0, c1, c2,              \
-                                                               static_cast<TT*>(dx), static_cast<TT*>(dz), nvec, c, relu)
+#define BWD_APPLY2(TT, UU, ST, MB, H2)                                                                                     \
+  bn_bwd_apply_kernel<TT, UU, ST, MB, H2><<<grid, kThreads, 0, s>>>(static_cast<const TT*>(dy), static_cast<const TT*>(dy2), \
+                                                                   static_cast<const TT*>(x), static_cast<const uint8_t*>(mask), \
+                                                                   c0, c1, c2, static_cast<TT*>(dx), static_cast<TT*>(dz), nvec, c, relu)
+#define BWD_APPLY(TT, UU, ST, MB) BWD_APPLY2(TT, UU, ST, MB, false)
+  if (dy2) {   // fork: gradient = dy + dy2 (6 streams)
+    static int fv = -1;
+    if (fv < 0) { const char* e = getenv("SPARKDL_BN_FORK_VARIANT"); fv = e ? atoi(e) : 0; }
+    if (dtype == 5) {
+      switch (fv) {
+        case 1: BWD_APPLY2(__nv_bfloat16, 2, false, 4, true); break;
+        case 2: BWD_APPLY2(__nv_bfloat16, 1, false, 4, true); break;
+        case 3: BWD_APPLY2(__nv_bfloat16, 2, true, 3, true); break;
+        default: BWD_APPLY2(__nv_bfloat16, 2, false, 3, true); break;
+      }
+    } else {
+      BWD_APPLY2(float, 2, true, 2, true);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   if (dtype == 5) {
     switch (variant) {
       case 1: BWD_APPLY(__nv_bfloat16, 2, true, 3); break;

@@ -10,6 +10,14 @@ import torch
 from torch import nn
 
 
+import os
+
+# Forked block outputs (see Bottleneck.forward): opt-in.  Measured on B200 (benchmarks/gpu_batch.sh forklab, round 2):
+# the in-kernel add removes autograd's add pass (1.3 ms / step) but the extra input stream costs the two backward
+# kernels of the largest BatchNorm layers more than that (21.5 ms / step at best vs 21.1 ms without).
+_FORK = os.environ.get("SPARKDL_BN_FORK", "0") == "1"
+
+
 class _ConvBN(nn.Module):
     """conv -> batch-norm (-> +residual) (-> ReLU) with an optional fused epilogue."""
 
@@ -23,15 +31,17 @@ class _ConvBN(nn.Module):
         self.fused = fused
         nn.init.kaiming_normal_(self.conv.weight, mode="fan_out", nonlinearity="relu")
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, fork=False):
         y = self.conv(x)
         if self.fused and y.is_cuda and self.training:
             from spark_deep_learning_b200.ops import norm
-            return norm.batch_norm_act(y, self.bn, residual, self.relu)
+            # num_batches_tracked of all layers is advanced by ResNet.forward in one batched op
+            return norm.batch_norm_act(y, self.bn, residual, self.relu, fork=fork, count_batches=False)
         y = self.bn(y)
         if residual is not None:
             y = y + residual
-        return torch.relu_(y) if self.relu else y
+        y = torch.relu_(y) if self.relu else y
+        return (y, y) if fork else y
 
 
 class Bottleneck(nn.Module):
@@ -48,8 +58,13 @@ class Bottleneck(nn.Module):
             self.down = _ConvBN(cin, cout, 1, stride=stride, relu=False, fused=fused)
 
     def forward(self, x):
-        idt = x if self.down is None else self.down(x)
-        return self.c(self.b(self.a(x)), residual=idt)
+        """``x`` is a tensor or a pair of tensors on one storage (the previous block's forked output): the first feeds
+        the convolution branch, the second the identity / downsample branch, so that the two gradients reach the
+        previous block's BatchNorm backward separately and are added inside its kernels (no autograd add pass).
+        Returns such a pair."""
+        xa, xi = x if isinstance(x, tuple) else (x, x)
+        idt = xi if self.down is None else self.down(xi)
+        return self.c(self.b(self.a(xa)), residual=idt, fork=_FORK)
 
 
 class ResNet(nn.Module):
@@ -77,7 +92,7 @@ class ResNet(nn.Module):
             if pool.stem_s2d_supported(x) and self.stem.conv.weight.dtype == torch.bfloat16:
                 w = pool.stem_s2d_weight(self.stem.conv.weight).contiguous(memory_format=torch.channels_last)
                 y = torch.nn.functional.conv2d(pool.stem_s2d(x), w)
-                return norm.batch_norm_act(y, self.stem.bn, None, True)
+                return norm.batch_norm_act(y, self.stem.bn, None, True, count_batches=False)
         if x.is_cuda and x.dtype != self.stem.conv.weight.dtype:
             x = x.to(dtype=self.stem.conv.weight.dtype, memory_format=torch.channels_last)
         return self.stem(x)
@@ -90,6 +105,13 @@ class ResNet(nn.Module):
         else:
             x = self.pool(x)
         x = self.blocks(x)
+        if isinstance(x, tuple):
+            x = x[0]
+        if self.fused and self.training and x.is_cuda:
+            nbt = [m.num_batches_tracked for m in self.modules()
+                   if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
+            if nbt:
+                torch._foreach_add_(nbt, 1)          # one launch for the 53 counters
         x = torch.flatten(torch.nn.functional.adaptive_avg_pool2d(x, 1), 1)
         return self.fc(x)
 

@@ -27,7 +27,7 @@ def _lib():
         lib.sdlc_bn_fwd.restype = i32
         lib.sdlc_bn_fwd.argtypes = [vp] * 13 + [i64, i32, f32, f32, i32, i32, u64]
         lib.sdlc_bn_bwd.restype = i32
-        lib.sdlc_bn_bwd.argtypes = [vp] * 14 + [i64, i32, i32, i32, u64]
+        lib.sdlc_bn_bwd.argtypes = [vp] * 15 + [i64, i32, i32, i32, i32, u64]
         _sig_done = True
     return lib
 
@@ -61,7 +61,7 @@ def supported(x):
 
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, momentum, eps, relu):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, momentum, eps, relu, fork=False):
         lib = _lib()
         n, c, h, w = x.shape
         m = n * h * w
@@ -81,49 +81,82 @@ class _BNAct(torch.autograd.Function):
         if rc != 0:
             raise RuntimeError("sdlc_bn_fwd failed (%d)" % rc)
         launch_counter.add(3)
-        ctx.save_for_backward(x, mask, weight, stats)
+        ctx.save_for_backward(x, mask, weight, bias, stats)
+        ctx.set_materialize_grads(False)             # an unused fork handle must not cost a zero tensor
         ctx.relu = relu
         ctx.has_res = residual is not None
+        if fork:
+            # two handles on the same storage: the consumers' gradients come back separately and are summed inside
+            # the backward kernels instead of by an autograd add pass (detach() = same storage, own autograd edge)
+            return y, y.detach()
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dy2=None):
         lib = _lib()
-        x, mask, weight, stats = ctx.saved_tensors
+        x, mask, weight, bias, stats = ctx.saved_tensors
+        if dy is None:
+            dy, dy2 = dy2, None
         n, c, h, w = x.shape
         m = n * h * w
         dev = x.device
         dy = dy.contiguous(memory_format=torch.channels_last)
+        if dy2 is not None:
+            dy2 = dy2.contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x)
         dz = torch.empty_like(x) if ctx.has_res else None
         red = torch.empty(5, c, dtype=torch.float32, device=dev)     # dweight, dbias, c0, c1, c2
         grid = lib.sdlc_bn_grid(m, c, _DT[x.dtype])
         ws = _workspace(dev, grid * 2 * c)
-        rc = lib.sdlc_bn_bwd(_p(dy), _p(x), _p(mask), _p(weight), _p(stats[0]), _p(stats[1]), _p(dx), _p(dz),
-                             _p(red[0]), _p(red[1]), _p(red[2]), _p(red[3]), _p(red[4]), _p(ws), m, c,
-                             1 if ctx.relu else 0, _DT[x.dtype], torch.cuda.current_stream(dev).cuda_stream)
+        # gradient sink (parallel/optimizer.py): the finalize kernel writes dweight / dbias straight into the gradient
+        # bucket views, no AccumulateGrad add per parameter
+        sinks = None
+        if weight is not None and bias is not None:
+            sw, sb = getattr(weight, "_sparkdl_grad_sink", None), getattr(bias, "_sparkdl_grad_sink", None)
+            if (sw is not None and sb is not None and weight.grad is not None and bias.grad is not None
+                    and weight.grad.dtype == torch.float32 and bias.grad.dtype == torch.float32
+                    and weight.grad.is_contiguous() and bias.grad.is_contiguous()):
+                sinks = (sw, sb)
+        dw_t, db_t = (weight.grad, bias.grad) if sinks else (red[0], red[1])
+        rc = lib.sdlc_bn_bwd(_p(dy), _p(dy2), _p(x), _p(mask), _p(weight), _p(stats[0]), _p(stats[1]), _p(dx), _p(dz),
+                             _p(dw_t), _p(db_t), _p(red[2]), _p(red[3]), _p(red[4]), _p(ws), m, c,
+                             1 if ctx.relu else 0, _DT[x.dtype], 1 if sinks else 0,
+                             torch.cuda.current_stream(dev).cuda_stream)
         if rc != 0:
             raise RuntimeError("sdlc_bn_bwd failed (%d)" % rc)
         launch_counter.add(3)
-        dw = red[0] if weight is not None else None
-        db = red[1] if weight is not None else None
-        return dx, dw, db, dz, None, None, None, None, None
+        if sinks:
+            sinks[0](weight)
+            sinks[1](bias)
+            dw = db = None
+        else:
+            dw = red[0] if weight is not None else None
+            db = red[1] if weight is not None else None
+        return dx, dw, db, dz, None, None, None, None, None, None
 
 
-def batch_norm_act(x, bn, residual=None, relu=True):
+def batch_norm_act(x, bn, residual=None, relu=True, fork=False, count_batches=True):
     """``relu(batch_norm(x) + residual)`` with training-mode statistics, fused.
 
     ``bn`` is a ``torch.nn.BatchNorm2d`` (its parameters / running stats are used and updated).
+    ``fork``: return the result twice (two tensors on one storage) for a consumer pair such as the next residual
+    block's first convolution and its identity branch - the two gradients are then added inside the backward kernels.
+    ``count_batches=False``: the caller advances ``num_batches_tracked`` itself (one batched op for all layers).
     Falls back to the unfused torch ops for layouts / dtypes the kernels do not cover."""
     if not bn.training or not supported(x) or (residual is not None and residual.dtype != x.dtype):
-        y = bn(x)
+        if bn.training and not count_batches:
+            y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, True,
+                                               bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+        else:
+            y = bn(x)
         if residual is not None:
             y = y + residual
-        return torch.relu(y) if relu else y
+        y = torch.relu(y) if relu else y
+        return (y, y) if fork else y
     momentum = bn.momentum if bn.momentum is not None else 0.1
-    if bn.track_running_stats and bn.num_batches_tracked is not None:
+    if count_batches and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     w = bn.weight.float() if bn.weight is not None and bn.weight.dtype != torch.float32 else bn.weight
     b = bn.bias.float() if bn.bias is not None and bn.bias.dtype != torch.float32 else bn.bias
     return _BNAct.apply(x, w, b, residual, bn.running_mean if bn.track_running_stats else None,
-                        bn.running_var if bn.track_running_stats else None, momentum, bn.eps, relu)
+                        bn.running_var if bn.track_running_stats else None, momentum, bn.eps, relu, fork)

@@ -26,6 +26,21 @@ from spark_deep_learning_b200.utils.config import get_config
 _ALIGN = 128  # bytes; every parameter starts on a 128-byte boundary inside its bucket
 
 
+def _view_like(flat, off, p):
+    """View of ``flat[off : off + p.numel()]`` with ``p``'s shape AND memory layout.  A channels-last convolution weight
+    keeps its channels-last strides inside the bucket: the parameter stays in the layout the convolution kernels want
+    (no per-step weight transposes) and the gradient accumulation into the bucket is a dense, vectorised add instead
+    of a strided one.  Element order inside a bucket is irrelevant to the (elementwise) reduction and optimizer."""
+    seg = flat[off:off + p.numel()]
+    if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+        return seg.as_strided(p.shape, p.stride())
+    return seg.view_as(p)
+
+
+def _layout_tag(p):
+    return "cl" if (p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last)) else "c"
+
+
 class _Bucket(object):
     __slots__ = ("index", "params", "offsets", "numel", "dtype", "device", "flat", "sym",
                  "pending", "launched", "handle", "done_event", "pflat", "psym", "state")
@@ -141,7 +156,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             else:
                 b.flat = torch.zeros(b.numel, dtype=b.dtype, device=b.device)
             for p, off in zip(b.params, b.offsets):
-                view = b.flat[off:off + p.numel()].view_as(p)
+                view = _view_like(b.flat, off, p)
                 if p.grad is not None:
                     view.copy_(p.grad)
                 p.grad = view
@@ -149,7 +164,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 self._grad_ptr[id(p)] = view.data_ptr()
                 self._passes[id(p)] = 0
                 if b.pflat is not None:
-                    pv = b.pflat[off:off + p.numel()].view_as(p)
+                    pv = _view_like(b.pflat, off, p)
                     pv.copy_(p.data)
                     p.data = pv
             b.pending = len(b.params)
@@ -204,7 +219,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             if g.data_ptr() != expected[pid]:
                 # someone replaced .grad (zero_grad(set_to_none=True), an AMP unscale copy ...):
                 # fold it back into the bucket and re-alias
-                view = b.flat[off:off + p.numel()].view_as(p)
+                view = _view_like(b.flat, off, p)
                 view.copy_(g)
                 p.grad = view
             n = passes[pid] + 1
@@ -354,7 +369,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             for b in self._buckets:
                 for p, off in zip(b.params, b.offsets):
                     if p.grad is None or p.grad.data_ptr() != self._grad_ptr[id(p)]:
-                        p.grad = b.flat[off:off + p.numel()].view_as(p)
+                        p.grad = _view_like(b.flat, off, p)
         bucketed = set(self._bucket_of)
         for g in self.param_groups:
             for p in g["params"]:
@@ -378,7 +393,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             fused["steps"][gi] = float(comm.fused_hyper(self, gi)["dev"][9].item())
         for b in self._buckets:
             st = comm.fused_state(self, b)
-            entry = {"numel": b.numel, "dtype": str(b.dtype)}
+            # the sharded state is stored in bucket order, which follows each parameter's memory layout (_view_like)
+            entry = {"numel": b.numel, "dtype": str(b.dtype), "layout": [_layout_tag(p) for p in b.params]}
             for k in ("s1", "s2", "master"):
                 if st[k] is None:
                     entry[k] = None
@@ -400,6 +416,11 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             raise ValueError("checkpoint has %d buckets, this optimizer %d (different bucket_bytes?)"
                              % (len(fused["buckets"]), len(self._buckets)))
         for b, entry in zip(self._buckets, fused["buckets"]):
+            want = [_layout_tag(p) for p in b.params]
+            if entry.get("layout", want) != want:
+                raise ValueError("checkpoint bucket %d was saved with a different parameter memory layout "
+                                 "(channels_last vs contiguous); convert the model the same way before "
+                                 "building the optimizer" % b.index)
             st = comm.fused_state(self, b)
             lo, n = st["lo"], st["n"]
             for k in ("s1", "s2", "master"):

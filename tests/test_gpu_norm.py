@@ -62,6 +62,59 @@ def test_bn_act_forward_backward(c, hw, n, dtype, with_res, relu):
     assert torch.allclose(bn.running_mean, 0.1 * m, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("c,hw,n", [(256, 14, 8), (64, 28, 5), (2048, 7, 2)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("use_both", [True, False])
+def test_bn_act_fork_adds_the_two_gradients_in_the_kernels(c, hw, n, dtype, use_both):
+    """fork=True returns two handles on one storage; their gradients are summed inside bn_bwd_reduce / bn_bwd_apply.
+    Result must equal the plain op fed with g1 + g2 (and with g1 alone when the second handle is unused)."""
+    from spark_deep_learning_b200.ops import norm
+    torch.manual_seed(1)
+    x = (torch.randn(n, c, hw, hw, device="cuda") * 2).to(dtype).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(n, c, hw, hw, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    g1 = torch.randn(n, c, hw, hw, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    g2 = torch.randn(n, c, hw, hw, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    grads = []
+    for fork in (True, False):
+        bn = torch.nn.BatchNorm2d(c).cuda()
+        xa, ra = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        if fork:
+            y1, y2 = norm.batch_norm_act(xa, bn, ra, True, fork=True)
+            assert y1.data_ptr() == y2.data_ptr()
+            if use_both:
+                torch.autograd.backward([y1, y2], [g1, g2])
+            else:
+                y1.backward(g1)
+        else:
+            y1 = norm.batch_norm_act(xa, bn, ra, True)
+            y1.backward((g1.float() + g2.float()).to(dtype) if use_both else g1)
+        grads.append((y1.detach().float(), xa.grad.float(), ra.grad.float(), bn.weight.grad.clone(), bn.bias.grad.clone()))
+    tol = 3e-2 if dtype == torch.bfloat16 else 1e-4      # bf16: the unfused arm rounds g1 + g2 to bf16 first
+    for a, b in zip(*grads):
+        assert (a - b).abs().max().item() <= tol * (b.abs().max().item() + 1e-6), (a - b).abs().max().item()
+
+
+def test_bn_grad_sink_accumulates_into_the_bucket_views():
+    """With a gradient sink on the BatchNorm parameters (DistributedOptimizer), bn_bwd_finalize adds dweight / dbias
+    straight into ``param.grad`` and autograd sees no gradient tensor."""
+    from spark_deep_learning_b200.ops import norm
+    torch.manual_seed(2)
+    c = 128
+    x = torch.randn(4, c, 14, 14, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    g = torch.randn_like(x)
+    ref_bn = torch.nn.BatchNorm2d(c).cuda()
+    norm.batch_norm_act(x.clone().requires_grad_(True), ref_bn, None, True).backward(g)
+    bn = torch.nn.BatchNorm2d(c).cuda()
+    calls = []
+    for p in (bn.weight, bn.bias):
+        p.grad = torch.full_like(p, 2.0)                    # pre-existing content: the sink must add to it
+        p._sparkdl_grad_sink = lambda q: calls.append(q)
+    norm.batch_norm_act(x.clone().requires_grad_(True), bn, None, True).backward(g)
+    assert len(calls) == 2 and calls[0] is bn.weight and calls[1] is bn.bias
+    assert torch.allclose(bn.weight.grad, ref_bn.weight.grad + 2.0, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(bn.bias.grad, ref_bn.bias.grad + 2.0, rtol=1e-5, atol=1e-5)
+
+
 def test_resnet_fused_matches_unfused():
     from spark_deep_learning_b200 import models
     torch.manual_seed(0)
