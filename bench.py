@@ -116,7 +116,7 @@ def main():
         "loss": res.get("loss"),
     }
     if args.impl == "ours":
-        out["runtime"] = {k: res.get(k) for k in ("transport", "multicast", "buckets", "cuda_graph")}
+        out["runtime"] = {k: res.get(k) for k in ("transport", "multicast", "buckets", "cuda_graph", "h2d_gbps", "numa")}
     else:
         out["reference_note"] = ("unmodified sparkdl 2.2.0-db1 HorovodRunner (in-process run); gradient exchange = "
                                  "torch DDP over NCCL 2.28.9, the NCCL-via-torch stand-in for horovod+NCCL")

@@ -50,6 +50,18 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
         return model(x, labels=y)          # bf16 parameters, fp32 master weights in the fused optimizer
 
     dx, dy = host_x.to(dev), host_y.to(dev)
+    # diagnostic for the end-to-end number: pinned host -> device bandwidth of this rank's input buffer (untimed region)
+    torch.cuda.synchronize()
+    hvd.barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        dx.copy_(host_x, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * host_x.numel() * host_x.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    from spark_deep_learning_b200.utils import affinity
+    numa = affinity.bind_to_gpu(dev.index)
 
     def step(x, y):
         opt.zero_grad()
@@ -120,6 +132,8 @@ def train(model_name="resnet50", batch=256, steps=20, warmup=5, e2e_steps=None, 
            "d2h_bytes": 4, "e2e_wall_ms": e2e_wall_ms, "loss": loss_val, "world": world, "batch": batch,
            "gpu_launches": int(launches),
            "transport": getattr(comm, "transport", None), "multicast": getattr(comm, "multicast", None),
-           "buckets": len(opt.bucket_summary()), "cuda_graph": graphed}
+           "buckets": len(opt.bucket_summary()), "cuda_graph": graphed,
+           "h2d_gbps": round(float(hvd.allreduce(torch.tensor([h2d_gbps], dtype=torch.float64), op=hvd.Min)[0]), 1),
+           "numa": numa}
     hvd.shutdown()
     return res

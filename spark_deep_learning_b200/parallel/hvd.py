@@ -86,6 +86,8 @@ def init(comm=None, process_sets=None):  # pylint: disable=unused-argument
         use_cuda = torch.cuda.is_available() and os.environ.get("SPARKDL_FORCE_CPU") != "1"
         if use_cuda:
             torch.cuda.set_device(ctx.local_rank % torch.cuda.device_count())
+            from spark_deep_learning_b200.utils import affinity
+            _S.affinity = affinity.bind_to_gpu(torch.cuda.current_device())   # external gangs (torchrun) get it here
         if ctx.rank == 0:
             shm_name = "/sparkdl-%s-%s" % (ctx.job_id[:40], uuid.uuid4().hex[:8])
             ctx.store.set("shm_name", shm_name)

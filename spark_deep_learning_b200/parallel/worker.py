@@ -52,7 +52,10 @@ def _pin_device():
     try:
         import torch
         if torch.cuda.is_available():
-            torch.cuda.set_device(int(os.environ.get("SPARKDL_LOCAL_RANK", "0")) % torch.cuda.device_count())
+            idx = int(os.environ.get("SPARKDL_LOCAL_RANK", "0")) % torch.cuda.device_count()
+            torch.cuda.set_device(idx)
+            from spark_deep_learning_b200.utils import affinity
+            affinity.bind_to_gpu(idx)          # threads + pinned host buffers on the GPU's own socket
     except Exception:  # pylint: disable=broad-except
         pass
 
