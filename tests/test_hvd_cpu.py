@@ -192,6 +192,53 @@ def test_distributed_optimizer_matches_single_process():
     assert diff < 1e-5 and nb >= 2
 
 
+def test_distributed_optimizer_keeps_channels_last_weights_inside_the_buckets():
+    """Bucket views keep a parameter's memory layout: a channels-last convolution weight stays channels-last (dense
+    gradient accumulation, no per-step transposes) and training matches a single-process replica."""
+    def main():
+        import torch
+        import sparkdl.hvd as hvd
+        hvd.init()
+        r, n = hvd.rank(), hvd.size()
+        torch.manual_seed(0)
+
+        def make():
+            return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 4, 1),
+                                       torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(4, 2))
+        model, ref = make().to(memory_format=torch.channels_last), make()
+        ref.load_state_dict(model.state_dict())
+        w = model[0].weight
+        assert not w.is_contiguous() and w.is_contiguous(memory_format=torch.channels_last)
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9),
+                                       named_parameters=model.named_parameters(), bucket_bytes=512)
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9)
+        hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+        layout = (w.grad.stride() == w.stride() and w.grad.is_contiguous(memory_format=torch.channels_last)
+                  and model[2].weight.grad.is_contiguous())           # 1x1 kernel: both layouts coincide
+        g = torch.Generator().manual_seed(5)
+        X = torch.randn(4 * n, 3, 6, 6, generator=g)
+        Y = torch.randn(4 * n, 2, generator=g)
+        for _ in range(3):
+            opt.zero_grad()
+            ((model(X[4 * r:4 * r + 4].contiguous(memory_format=torch.channels_last)) - Y[4 * r:4 * r + 4]) ** 2).mean().backward()
+            opt.step()
+            ropt.zero_grad()
+            ((ref(X) - Y) ** 2).mean().backward()
+            ropt.step()
+        diff = max((a - b).abs().max().item() for a, b in zip(model.parameters(), ref.parameters()))
+        return diff, layout, w.grad.stride() == w.stride()
+    diff, layout, still = HorovodRunner(np=-2).run(main)
+    assert layout and still and diff < 1e-5, (diff, layout, still)
+
+
+def test_cpu_affinity_helper_parses_sysfs_lists_and_never_raises():
+    from spark_deep_learning_b200.utils import affinity
+    assert affinity._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert affinity._parse_cpulist("") == set()
+    info = affinity.bind_to_gpu(0)                   # no GPU here: nothing is bound, nothing raises
+    assert info["bound"] is False and affinity.bind_to_gpu(0) is info
+
+
 def test_dead_peer_fails_job_quickly():
     def main():
         import os
