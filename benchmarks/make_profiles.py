@@ -126,7 +126,9 @@ def allreduce_section(lines):
             np_, d["info"]["transport"], d["info"]["multicast"]),
             "busbw = 2(N-1)/N x bytes / t.  `LL` = barrier-free flag-in-data kernel (<= 64 KB), `one-shot` / `p2p` = peer "
             "ld/st kernels, `nvls` = multimem.ld_reduce / multimem.st kernel, `wire` = 16-bit / block-scaled fp8 wire "
-            "formats of an fp32 tensor, NCCL = torch.distributed (2.28.9) on the same GPUs.\n",
+            "formats of an fp32 tensor, NCCL = torch.distributed (2.28.9) on the same GPUs."
+            + ("  The `nvls` column of this np=8 run used 32 CTAs; the sweep's CTA variants (JSON keys `nvls_ctas16_busbw` ...) "
+               "showed 16 CTAs to be faster up to 64 MB (32 MB: 90.5 us instead of 98.7), which is now the default.\n" if np_ == 8 else "\n"),
             "| dtype | bytes | LL us | one-shot us | p2p us | nvls us | wire bf16 us | wire fp8 us | NCCL us | best busbw GB/s | NCCL busbw | best / NCCL |",
             "|---|---|---|---|---|---|---|---|---|---|---|---|"]
         for r in d["rows"]:
@@ -151,6 +153,10 @@ def collective_section(lines):
                   "`torch.distributed` NCCL collectives on preallocated tensors; the engine adds a negotiation round trip "
                   "and a staging copy per call, so small messages are slower than NCCL here (the symmetric-buffer kernels "
                   "above are the fast path the optimizer uses).\n",
+                  ("Note: this np=%d table was taken before `hvd.allgather` stopped doing a blocking host-side size exchange per "
+                   "call (one negotiation now, see the np=2 table, taken after) and before the benchmark warmed the "
+                   "allocator with the same number of operations in flight; no 8-GPU budget was left to repeat it.\n" % np_)
+                  if np_ in (4, 8) else "",
                   "| bytes | allgather ours us | NCCL us | broadcast ours us | NCCL us | reducescatter ours us | NCCL us |", "|---|---|---|---|---|---|---|"]
         for r in d["rows"]:
             lines.append("| %d | %s | %s | %s | %s | %s | %s |" % (
