@@ -20,6 +20,7 @@ import io
 import os
 import pickle
 import threading
+import weakref
 import uuid
 
 import torch
@@ -57,6 +58,9 @@ class _State(object):
         self.comm = None          # ops.comm.SymmComm when CUDA is in use
         self.counters = {}
         self.lock = threading.Lock()
+        self.inflight = {}        # key -> (weakref to the handle, engine handles, tensors kept alive, is_cuda)
+        self.inflight_seq = 0
+        self.inflight_purge_at = 64
 
 
 _S = _State()
@@ -112,6 +116,10 @@ def shutdown():
             return
         _S.initialized = False
         try:
+            _purge_inflight(wait=True)       # operations whose handles were dropped still own their tensors
+        except Exception:  # pylint: disable=broad-except
+            pass
+        try:
             if _S.comm is not None:
                 _S.comm.close()
         finally:
@@ -120,6 +128,7 @@ def shutdown():
                 _S.engine.shutdown()
             finally:
                 _S.engine = None
+                _S.inflight.clear()          # only now: the engine thread is gone, nobody writes the tensors any more
                 _S.ctx = None   # the job context (store connection) stays alive for a later init()
 
 
@@ -338,7 +347,7 @@ class Compression(object):
 # handles
 # ---------------------------------------------------------------------------------------------
 class _Handle(object):
-    __slots__ = ("hs", "output", "keep", "post", "cuda", "done", "result")
+    __slots__ = ("hs", "output", "keep", "post", "cuda", "done", "result", "key", "__weakref__")
 
     def __init__(self, hs, output, keep, post=None, cuda=False):
         self.hs = hs
@@ -348,6 +357,57 @@ class _Handle(object):
         self.cuda = cuda
         self.done = False
         self.result = None
+        self.key = None
+        if hs:
+            _track(self)
+
+
+# ---------------------------------------------------------------------------------------------
+# In-flight registry.  The engine thread reads the input and writes the output of an asynchronous operation until it
+# completes, whatever the caller does with the returned handle.  A handle that is dropped without synchronize() (or
+# overwritten by the next iteration's list) must therefore not take its tensors with it: the registry keeps them alive
+# until the engine reports completion, and frees the engine-side state of handles nobody will synchronize any more.
+# (Found with a CPU soak test: 64 dropped allreduce handles -> the engine wrote into freed tensors -> heap corruption.)
+# ---------------------------------------------------------------------------------------------
+def _track(handle):
+    reg = _S.inflight
+    _S.inflight_seq += 1
+    handle.key = _S.inflight_seq             # not id(): ids are recycled while the old operation may still be running
+    reg[handle.key] = (weakref.ref(handle), tuple(handle.hs), handle.keep, handle.cuda)
+    if len(reg) >= _S.inflight_purge_at:
+        _purge_inflight()
+        _S.inflight_purge_at = max(64, 2 * len(reg))
+
+
+def _purge_inflight(wait=False):
+    """Forget completed operations; release those whose handle object is gone.  ``wait``: give each up to 5 s to
+    complete first (shutdown path); entries that still have not completed stay registered."""
+    eng = _S.engine
+    if eng is None:
+        return
+    patience = wait
+    for key, (ref, hs, _keep, cuda) in list(_S.inflight.items()):
+        if patience:
+            for h in hs:
+                try:
+                    eng.wait(h, timeout=5.0)
+                except TimeoutError:
+                    patience = False         # a peer is gone: do not wait for the rest either
+                except Exception:  # pylint: disable=broad-except
+                    pass
+        if not all(eng.poll(h) != 0 for h in hs):
+            continue
+        if ref() is None:                    # dropped by the caller: nobody else will release it
+            for h in hs:
+                if cuda and _S.comm is not None:
+                    try:
+                        ev = eng.done_event(h)
+                        if ev:
+                            _S.comm.current_stream_wait(ev, release=True)   # order the buffers' reuse after the kernel
+                    except Exception:  # pylint: disable=broad-except
+                        pass
+                eng.release(h)
+        del _S.inflight[key]
 
 
 def _auto_name(kind, name):
@@ -436,6 +496,7 @@ def synchronize(handle):
     _require()
     if handle.done:
         return handle.result
+    _S.inflight.pop(handle.key, None)
     try:
         for h in handle.hs:
             try:

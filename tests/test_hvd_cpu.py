@@ -239,6 +239,32 @@ def test_cpu_affinity_helper_parses_sysfs_lists_and_never_raises():
     assert info["bound"] is False and affinity.bind_to_gpu(0) is info
 
 
+def test_dropped_async_handles_keep_their_tensors_until_the_engine_is_done():
+    """An async handle that is dropped without synchronize() must not free tensors the engine thread still writes
+    (a soak run used to corrupt the heap).  The frontend keeps them in an in-flight registry until completion."""
+    def main():
+        import gc
+        import time
+        import torch
+        import sparkdl.hvd as hvd
+        from spark_deep_learning_b200.parallel import hvd as H
+        hvd.init()
+        for rep in range(40):                                   # 40 x 32 operations whose handles are dropped at once
+            for i in range(32):
+                hvd.allreduce_async(torch.full((4096,), float(i)), name="drop.%d.%d" % (rep, i))
+            gc.collect()
+        tracked = len(H._S.inflight)
+        ok = hvd.allreduce(torch.ones(3), op=hvd.Sum, name="after")[0].item() == hvd.size()
+        hvd.barrier()
+        deadline = time.time() + 20
+        while H._S.inflight and time.time() < deadline:
+            H._purge_inflight()
+            time.sleep(0.01)
+        return tracked, len(H._S.inflight), ok
+    tracked, left, ok = HorovodRunner(np=-2).run(main)
+    assert ok and tracked > 0 and left == 0, (tracked, left, ok)
+
+
 def test_dead_peer_fails_job_quickly():
     def main():
         import os
