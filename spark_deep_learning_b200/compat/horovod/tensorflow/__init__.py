@@ -77,4 +77,5 @@ def broadcast_variables(variables, root_rank=0):
 
 
 def broadcast_object(obj, root_rank=0, name=None):
+    """cloudpickle ``obj`` on ``root_rank`` and return it on every rank (``hvd.broadcast_object``)."""
     return _hvd.broadcast_object(obj, root_rank, name)
