@@ -322,6 +322,21 @@ class _XgboostModel(Model, _XgboostParams, MLReadable, MLWritable):
     def evals_result(self):
         return self._evals_result
 
+    def get_feature_importances(self, importance_type="weight"):
+        """``{"f<index>": score}`` as ``Booster.get_score`` (``weight``, ``gain``, ``cover``, ``total_gain``,
+        ``total_cover``); the model's ``importance_type`` param is the default of :attr:`feature_importances_`."""
+        return self._xgb_sklearn_model.get_score(importance_type=importance_type)
+
+    @property
+    def feature_importances_(self):
+        """Normalised dense importance vector (``XGBModel.feature_importances_`` semantics)."""
+        kind = "gain"
+        try:
+            kind = self.getOrDefault("importance_type") or "gain"
+        except Exception:  # pylint: disable=broad-except
+            pass
+        return self._xgb_sklearn_model.feature_importances(kind)
+
     def _margins(self, fr):
         import torch
         gv = self.getOrDefault

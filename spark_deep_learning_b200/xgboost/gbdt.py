@@ -409,14 +409,40 @@ class Booster(object):
             out.append("\n".join(lines))
         return out
 
-    def get_score(self, importance_type="weight"):
-        sc = {}
+    def get_score(self, fmap="", importance_type="weight"):
+        """Feature importance as ``xgboost.Booster.get_score``: ``weight`` (number of splits on the feature), ``gain`` /
+        ``cover`` (average loss reduction / average hessian mass of those splits), ``total_gain``, ``total_cover``.
+        Features that are never used are absent.  ``fmap`` is accepted for signature compatibility."""
+        if fmap not in ("", None) and importance_type == "weight" and fmap in ("weight", "gain", "cover", "total_gain", "total_cover"):
+            importance_type = fmap                   # get_score("gain"): positional use of the pre-2.0 signature
+        if importance_type not in ("weight", "gain", "cover", "total_gain", "total_cover"):
+            raise ValueError("unknown importance_type %r" % (importance_type,))
+        count, gain, cover = {}, {}, {}
         for t in self.trees:
             for i, f in enumerate(t.feature):
                 if t.left[i] >= 0:
                     k = "f%d" % f
-                    sc[k] = sc.get(k, 0.0) + (1.0 if importance_type == "weight" else t.gain[i])
-        return sc
+                    count[k] = count.get(k, 0) + 1
+                    gain[k] = gain.get(k, 0.0) + float(t.gain[i])
+                    cover[k] = cover.get(k, 0.0) + float(t.cover[i])
+        if importance_type == "weight":
+            return {k: float(v) for k, v in count.items()}
+        if importance_type == "total_gain":
+            return gain
+        if importance_type == "total_cover":
+            return cover
+        src = gain if importance_type == "gain" else cover
+        return {k: src[k] / count[k] for k in count}
+
+    def feature_importances(self, importance_type="gain"):
+        """Dense, normalised importance vector of length ``n_features`` (what ``XGBModel.feature_importances_`` holds)."""
+        sc = self.get_score(importance_type=importance_type)
+        n = int(self.n_features) if self.n_features else (max([int(k[1:]) for k in sc] + [-1]) + 1)
+        v = np.zeros(n, dtype=np.float32)
+        for k, x in sc.items():
+            v[int(k[1:])] = x
+        tot = float(v.sum())
+        return v / tot if tot > 0 else v
 
     # -- inference ------------------------------------------------------------------------------------
     def _pack(self, device, ntree_limit=None):

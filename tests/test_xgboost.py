@@ -560,6 +560,29 @@ def test_real_values_never_land_in_the_missing_bin():
     assert int((bins[:, 0] == gbdt.MISSING_BIN).sum()) == 0
 
 
+def test_get_score_importance_types_follow_xgboost_semantics():
+    from spark_deep_learning_b200.xgboost import gbdt
+    rng = np.random.RandomState(3)
+    X = rng.randn(3000, 6).astype(np.float32)
+    y = (3 * X[:, 0] + np.sin(2 * X[:, 1]) + 0.05 * rng.randn(3000)).astype(np.float32)     # features 2..5 are noise
+    b, _ = gbdt.train(dict(n_estimators=10, max_depth=4, learning_rate=0.3), X, y)
+    w, g, c = b.get_score(), b.get_score(importance_type="gain"), b.get_score(importance_type="cover")
+    tg, tc = b.get_score(importance_type="total_gain"), b.get_score(importance_type="total_cover")
+    assert set(w) == set(g) == set(c) == set(tg) == set(tc) and "f0" in w
+    for k in w:
+        assert w[k] >= 1 and abs(g[k] * w[k] - tg[k]) <= 1e-4 * max(1.0, tg[k]) and abs(c[k] * w[k] - tc[k]) <= 1e-4 * max(1.0, tc[k])
+        assert 0 < c[k] <= 3000 + 1e-3                       # squared error: hessian mass = number of rows in the node
+    assert max(tg, key=tg.get) == "f0"                        # the dominant signal carries the largest total gain
+    from sparkdl.xgboost import XgboostRegressor
+    m = XgboostRegressor(n_estimators=5, max_depth=3, importance_type="total_gain").fit(
+        pd.DataFrame({"features": list(X[:500]), "label": y[:500]}))
+    assert int(np.argmax(m.feature_importances_)) == 0 and m.get_feature_importances("weight")["f0"] >= 1
+    imp = b.feature_importances("total_gain")
+    assert imp.shape == (6,) and abs(float(imp.sum()) - 1.0) < 1e-5 and int(imp.argmax()) == 0
+    with pytest.raises(ValueError):
+        b.get_score(importance_type="nope")
+
+
 def test_booster_round_trips_through_the_xgboost_json_schema(tmp_path):
     """ref xgboost.py:130-133: get_booster() is an xgboost Booster; interoperability is the JSON model schema."""
     import json
