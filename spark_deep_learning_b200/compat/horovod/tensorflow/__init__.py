@@ -15,7 +15,8 @@ from spark_deep_learning_b200.parallel.hvd import (Average, Max, Min, Product, S
                                                    is_initialized, local_rank, local_size, rank, shutdown, size)
 
 __all__ = ["init", "shutdown", "rank", "size", "local_rank", "local_size", "allreduce", "allgather", "broadcast",
-           "broadcast_variables", "broadcast_object", "Average", "Sum", "Min", "Max", "Product", "barrier"]
+           "broadcast_variables", "broadcast_object", "allgather_object", "grouped_allreduce", "DistributedGradientTape",
+           "Average", "Sum", "Min", "Max", "Product", "barrier"]
 
 
 def _tf():
@@ -79,3 +80,49 @@ def broadcast_variables(variables, root_rank=0):
 def broadcast_object(obj, root_rank=0, name=None):
     """cloudpickle ``obj`` on ``root_rank`` and return it on every rank (``hvd.broadcast_object``)."""
     return _hvd.broadcast_object(obj, root_rank, name)
+
+
+def allgather_object(obj, name=None):
+    """List with every worker's (cloudpickled) ``obj``, in rank order."""
+    return _hvd.allgather_object(obj, name=name)
+
+
+def grouped_allreduce(tensors, average=None, name=None, op=None):
+    """Allreduce a list of tensors as one negotiated group (the engine fuses them into one buffer)."""
+    arrs = [_to_numpy(t) for t in tensors]
+    outs = _hvd.grouped_allreduce([_torch(a) for a in arrs], average=average, name=name, op=op)
+    return [_like(o.numpy().reshape(a.shape), t) for o, a, t in zip(outs, arrs, tensors)]
+
+
+class DistributedGradientTape(object):
+    """``hvd.DistributedGradientTape(tape)``: wraps an object with ``gradient(target, sources, ...)`` (a
+    ``tf.GradientTape``) and averages the returned gradients over all workers - one grouped allreduce per call, ``None``
+    gradients stay ``None``.  Usable as a context manager when the wrapped tape is one."""
+
+    def __init__(self, gradtape, op=None, name=None):
+        self._tape = gradtape
+        self._op = Average if op is None else op
+        self._name = name or "DistributedGradientTape"
+        self._calls = 0
+
+    def __enter__(self):
+        self._tape.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self._tape.__exit__(*exc)
+
+    def __getattr__(self, item):                 # watch(), stop_recording(), ... go to the wrapped tape
+        return getattr(self._tape, item)
+
+    def gradient(self, target, sources, *args, **kwargs):
+        grads = self._tape.gradient(target, sources, *args, **kwargs)
+        single = not isinstance(grads, (list, tuple))
+        glist = [grads] if single else list(grads)
+        idx = [i for i, g in enumerate(glist) if g is not None]
+        self._calls += 1
+        if idx and size() > 1:
+            red = grouped_allreduce([glist[i] for i in idx], op=self._op, name="%s.%d" % (self._name, self._calls))
+            for i, g in zip(idx, red):
+                glist[i] = g
+        return glist[0] if single else (type(grads)(glist) if isinstance(grads, tuple) else glist)

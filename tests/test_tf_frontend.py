@@ -94,3 +94,42 @@ def test_keras_style_frontend_on_two_cpu_workers(monkeypatch):
     assert out["after_pass1"] == [0.0] and out["after_pass2"] == [-2.5]
     assert out["bgv"] == [[1.0, 1.0, 1.0], [[10.0, 10.0], [10.0, 10.0]]]
     assert out["metric"] == {"loss": 0.5, "acc": 1.0, "note": "x"}
+
+
+def _tape_main():
+    import numpy as np
+    from spark_deep_learning_b200 import compat
+    compat.install_horovod_shim()
+    import horovod.tensorflow as hvd                 # what an unmodified TF2 custom-loop main imports
+    hvd.init()
+    r, n = hvd.rank(), hvd.size()
+
+    class Tape(object):                               # stands in for tf.GradientTape
+        def __init__(self):
+            self.entered = 0
+
+        def __enter__(self):
+            self.entered += 1
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def watch(self, v):
+            self.watched = v
+
+        def gradient(self, target, sources):
+            return [np.full((2, 3), float(r + 1), dtype=np.float32), None, np.float32(10.0 * (r + 1))][:len(sources)]
+
+    with hvd.DistributedGradientTape(Tape()) as tape:
+        tape.watch("w")                               # forwarded to the wrapped tape
+    g = tape.gradient(None, ["a", "b", "c"])
+    single = hvd.DistributedGradientTape(Tape(), op=hvd.Sum).gradient(None, ["a"])
+    objs = hvd.allgather_object({"rank": r})
+    mean = sum(range(1, n + 1)) / n
+    return (float(g[0][0, 0]), g[1], float(g[2]), float(single[0][0, 0]), [o["rank"] for o in objs], mean, tape._tape.watched)
+
+
+def test_distributed_gradient_tape_averages_the_gradients():
+    g0, gnone, g2, ssum, ranks, mean, watched = HorovodRunner(np=-2).run(_tape_main)
+    assert g0 == mean and gnone is None and g2 == 10.0 * mean and ssum == 3.0 and ranks == [0, 1] and watched == "w"
