@@ -107,6 +107,20 @@ def init(comm=None, process_sets=None):  # pylint: disable=unused-argument
             fn, cctx = _S.comm.engine_executor()
             _S.engine.set_gpu_executor(fn, cctx)
         _S.initialized = True
+        if not getattr(_S, "atexit_registered", False):
+            import atexit
+            atexit.register(_shutdown_at_exit)
+            _S.atexit_registered = True
+
+
+def _shutdown_at_exit():
+    """A single-process script that forgets ``hvd.shutdown()`` would leave its 27 MB shared-memory segment behind.
+    Gangs are left alone here: their teardown is collective and is driven by the launcher / the user's code."""
+    try:
+        if _S.initialized and _S.ctx is not None and _S.ctx.size == 1:
+            shutdown()
+    except Exception:  # pylint: disable=broad-except
+        pass
 
 
 def shutdown():

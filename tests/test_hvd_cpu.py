@@ -1,5 +1,7 @@
 """T1/T3 - hvd frontend over the C++ engine + shm data plane, on CPU, multi-process
 (BASELINE.json config 1)."""
+import os
+
 import pytest
 
 from sparkdl import HorovodRunner
@@ -264,6 +266,19 @@ def test_dropped_async_handles_keep_their_tensors_until_the_engine_is_done():
         return tracked, len(H._S.inflight), ok
     tracked, left, ok = HorovodRunner(np=-2).run(main)
     assert ok and tracked >= 32 and left == 0, (tracked, left, ok)
+
+
+def test_single_process_script_without_shutdown_leaves_no_shared_memory_behind():
+    import glob
+    import subprocess
+    import sys
+    before = set(glob.glob("/dev/shm/sparkdl-single*"))
+    code = ("import torch, sparkdl.hvd as hvd; hvd.init(); "
+            "print(float(hvd.allreduce(torch.ones(3), op=hvd.Sum)[0]))")          # no hvd.shutdown()
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and r.stdout.strip() == "1.0", r.stderr[-500:]
+    assert set(glob.glob("/dev/shm/sparkdl-single*")) - before == set()
 
 
 def test_dead_peer_fails_job_quickly():
