@@ -70,6 +70,10 @@ class JobContext(object):
             self.store.close()
         except Exception:  # pylint: disable=broad-except
             pass
+        if getattr(self, "mode", None) == "external" and self.rank == 0 and \
+                os.path.basename(self.job_dir).startswith("sparkdl-ext-"):
+            import shutil
+            shutil.rmtree(self.job_dir, ignore_errors=True)     # created by this rank (_private_dir)
         if self._server is not None:
             self._server.close()
             self._server = None

@@ -87,7 +87,11 @@ def leave_gang(ctx, server):
         _context.reset_context()
         ctx.barrier()
         if server is not None:
+            job_dir = os.path.dirname(server.path) if getattr(server, "path", None) else None
             server.close()
+            if job_dir and os.path.basename(job_dir).startswith("sparkdl-spark-"):
+                import shutil
+                shutil.rmtree(job_dir, ignore_errors=True)
 
 
 def launch_on_spark(spark, main, kwargs, num_proc):

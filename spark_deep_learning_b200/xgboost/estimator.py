@@ -510,7 +510,13 @@ def _spill_to_disk(X, digits):
     mm = np.memmap(path, dtype=np.float32, mode="w+", shape=Xr.shape)
     mm[:] = Xr
     mm.flush()
-    return np.memmap(path, dtype=np.float32, mode="r", shape=Xr.shape)
+    ro = np.memmap(path, dtype=np.float32, mode="r", shape=Xr.shape)
+    del mm
+    try:
+        os.unlink(path)          # the mapping keeps the pages; no file is left behind when training ends (or crashes)
+    except OSError:
+        pass
+    return ro
 
 
 def _worker_train(shards, train_args):
