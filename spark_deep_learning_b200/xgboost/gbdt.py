@@ -738,7 +738,7 @@ class _HistBuilder(object):
         return hist.view(n_nodes, self.F, MAX_BINS, 2)
 
 
-IGNORED_PARAMS = ("booster", "n_jobs", "importance_type", "tree_method")
+IGNORED_PARAMS = ("booster", "n_jobs", "tree_method")      # importance_type is honoured by feature_importances_
 
 DEFAULTS = dict(scale_pos_weight=1.0, n_estimators=100, max_depth=6, learning_rate=0.3, gamma=0.0, min_child_weight=1.0, subsample=1.0,
                 colsample_bytree=1.0, reg_lambda=1.0, reg_alpha=0.0, max_bin=256, base_score=0.5, random_state=0,
