@@ -31,7 +31,10 @@ static int run_rank(const std::string& shm, int rank, int world, int tensors) {
     return 2;
   }
   int bad = 0;
-  auto worker = [&](int tid) {
+  // Rounds 0-2 repeat the same names and shapes (rounds 1-2 go through the response cache: one bit per tensor instead of
+  // a request record); round 3 changes the length of every third tensor (cached signature no longer matches: the entry
+  // is demoted to the record path and re-established); round 4 repeats round 3's shapes (cache hits again).
+  auto worker = [&](int tid, int round) {
     std::vector<std::vector<float>> bufs;
     std::vector<int64_t> handles;
     std::vector<int> ids;
@@ -39,7 +42,8 @@ static int run_rank(const std::string& shm, int rank, int world, int tensors) {
       int i = (rank % 2 == 0) ? k : tensors - 1 - k;   // odd ranks submit in reverse order
       if (i % 2 != tid) continue;
       ids.push_back(i);
-      bufs.emplace_back(17 + i, (float)(rank + i));
+      const int len = 17 + i + ((round >= 3 && i % 3 == 0) ? 5 : 0);
+      bufs.emplace_back(len, (float)(rank + i));
     }
     for (size_t j = 0; j < ids.size(); ++j) {
       Request r;
@@ -68,9 +72,15 @@ static int run_rank(const std::string& shm, int rank, int world, int tensors) {
       eng.release(handles[j]);
     }
   };
-  std::thread t0(worker, 0), t1(worker, 1);
-  t0.join();
-  t1.join();
+  for (int round = 0; round < 5; ++round) {
+    std::thread t0(worker, 0, round), t1(worker, 1, round);
+    t0.join();
+    t1.join();
+  }
+  if (eng.cache_hits() == 0) {
+    fprintf(stderr, "rank %d: the response cache was never hit\n", rank);
+    ++bad;
+  }
   // one broadcast and one ragged allgather from the main thread
   {
     std::vector<int32_t> b(100, rank == 1 % world ? 7 : -1);
