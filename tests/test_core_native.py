@@ -82,6 +82,26 @@ def test_engine_stress_thread_sanitizer(tmp_path):
     assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("san", ["", "-fsanitize=address,undefined", "-fsanitize=thread"])
+def test_native_cpu_histogram_check_plain_and_sanitized(tmp_path, san):
+    """csrc/core/tests/gbdt_hist_check.cc: the feature-parallel histogram vs a serial reference (empty input, inactive
+    rows, 1-100 features, 1-64 nodes, 1 / 3 / default threads), also under ASan + UBSan and ThreadSanitizer."""
+    import os
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spark_deep_learning_b200", "csrc", "core")
+    exe = str(tmp_path / "gbdt_hist_check")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread"] + ([san, "-fno-omit-frame-pointer"] if san else []) + \
+        ["-o", exe, os.path.join(src, "tests", "gbdt_hist_check.cc"), os.path.join(src, "gbdt_cpu.cc")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        if san:
+            pytest.skip("sanitizer runtime not available: %s" % r.stderr[-200:])
+        raise AssertionError(r.stderr[-2000:])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+    assert "Sanitizer" not in r.stderr, r.stderr[-3000:]
+
+
 def test_native_cpu_histogram_matches_numpy():
     """sdl_gbdt_hist_cpu (feature-parallel, int64) against a plain numpy scatter-add; bad node ids are rejected."""
     import numpy as np
