@@ -18,7 +18,9 @@ OP_SUM, OP_AVERAGE, OP_MIN, OP_MAX, OP_PRODUCT = range(5)
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsparkdl_core.so")
+    """The engine library; ``SPARKDL_CORE_LIB`` points at an alternative build (e.g. one compiled with
+    ``-fsanitize=address`` for a sanitizer run of the Python test-suite)."""
+    return os.environ.get("SPARKDL_CORE_LIB") or os.path.join(_HERE, "libsparkdl_core.so")
 
 
 def load():
